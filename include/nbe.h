@@ -1,0 +1,134 @@
+/* nbe.h -- C ABI of the B200-native N-body emulator forward pass (libnbe_b200.so).
+ *
+ * Plain pointers and sizes only; no torch / CUDA types in the signatures (streams are passed
+ * as void* holding a cudaStream_t).  Every function returns 0 (NBE_OK) or a negative error
+ * code and never throws; nbe_last_error() gives the message.  The caller owns every I/O
+ * buffer; the context owns the packed weights, the activation arena and its streams.  One
+ * context per (GPU, host thread); contexts are independent.
+ *
+ * The reference (/root/reference, pure JAX/Flax) has no FFI of its own: its operator
+ * boundary is `jax.jit(model.apply)` (src/jax_nbody_emulator/subbox.py:137, called at
+ * :221-233) and `NBodyEmulator.apply` (nbody_emulator.py:42-79).  Each entry point below
+ * cites the reference interface it stands in for; INTEGRATION.md shows the jax.ffi / ctypes
+ * stub a maintainer of the reference would add.
+ */
+#ifndef NBE_H_
+#define NBE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBE_OK 0
+#define NBE_ERR_ARG (-1)      /* bad argument (shape, dtype, null pointer, state)        */
+#define NBE_ERR_CUDA (-2)     /* a CUDA runtime / driver call failed                     */
+#define NBE_ERR_STATE (-3)    /* call order: params / modulation missing                 */
+#define NBE_ERR_UNSUPPORTED (-4)
+
+/* element types of caller-visible buffers */
+enum { NBE_F32 = 0, NBE_F16 = 1, NBE_BF16 = 2 };
+
+/* arithmetic of the conv layers.
+ * NBE_PREC_SPLIT  (default): primal activations and weights are carried as fp16 hi+lo pairs
+ *   (3 tensor-core products, ~22 significant bits), tangent in fp16; fp32 accumulation in
+ *   TMEM.  Needed to meet rel-L2 <= 1e-3 on the *velocity*: the LeakyReLU tangent rule
+ *   (layers_vel.py:185) is discontinuous in the primal sign, so a primal rounding of
+ *   relative size d flips a fraction ~d of the masks and costs ~sqrt(d) in velocity.
+ * NBE_PREC_FP16: single fp16 product (displacement ~5e-4, velocity ~1e-2 rel-L2).        */
+enum { NBE_PREC_SPLIT = 0, NBE_PREC_FP16 = 1 };
+
+typedef struct nbe_ctx nbe_ctx;
+
+/* One conv layer of the parameter tree params['params'][block][layer]
+ * (nbody_emulator.py:115-129; leaf shapes tests/test_style_layers_vel.py:392-436).
+ * All pointers are HOST fp32, C-contiguous.  Style models: style_weight (cin,2) and
+ * style_bias (cin) set, dweight NULL.  Premodulated models: style_* NULL, weight is the
+ * demodulated weight and dweight its Dz-tangent (NULL when compute_vel == 0).            */
+typedef struct nbe_layer_params {
+  const char* block;          /* "conv_l00", "down_l0", ... "conv_r01" */
+  const char* layer;          /* "skip", "conv_0", "conv_1"            */
+  const float* weight;        /* (cout, cin, k, k, k)                  */
+  const float* dweight;       /* (cout, cin, k, k, k) or NULL          */
+  const float* bias;          /* (cout)                                */
+  const float* style_weight;  /* (cin, 2) or NULL                      */
+  const float* style_bias;    /* (cin) or NULL                         */
+  int32_t cout, cin, k;
+} nbe_layer_params;
+
+/* Create / destroy a per-GPU context (replaces the implicit default-device state behind
+ * jax.jit at subbox.py:137). */
+int nbe_create(nbe_ctx** out, int device);
+void nbe_destroy(nbe_ctx* ctx);
+const char* nbe_last_error(const nbe_ctx* ctx);
+const char* nbe_version(void);
+
+/* Upload the 33-layer parameter tree (replaces `params` in model.apply(params, ...),
+ * subbox.py:226-233).  premodulated: 0 = Style* models, 1 = NBodyEmulator(Vel)Core.
+ * compute_vel: 1 = *VelCore.  eps: demodulation epsilon (style_layers_vel.py:33).        */
+int nbe_set_params(nbe_ctx* ctx, const nbe_layer_params* layers, int n_layers, int premodulated,
+                   int compute_vel, float eps);
+int nbe_set_precision(nbe_ctx* ctx, int precision);
+
+/* Per-sample weight modulation + demodulation + Dz-tangent for `batch` samples
+ * (style_layers_vel.py:62-105; nbody_emulator.py:131-148, :189-219), one fused kernel over
+ * all layers, writing the tensor-core operand layout.  Om may be NULL for premodulated
+ * models (the weights are only re-packed).  Host arrays of length `batch`.               */
+int nbe_modulate(nbe_ctx* ctx, const float* Om, const float* Dz, int batch, void* stream);
+
+/* Read back the fp32 modulated weight / dweight of one layer and sample in OIDHW order
+ * (backs modulate_emulator_parameters(_vel), nbody_emulator.py:150-187, :221-266).
+ * dw_host may be NULL.  Requires a prior nbe_modulate.                                   */
+int nbe_get_modulated(nbe_ctx* ctx, int layer_index, int sample, float* w_host, float* dw_host);
+
+/* model.apply on device buffers (the four *Core.__call__; e.g.
+ * style_nbody_emulator_vel_core.py:105-195): x_dev (batch,3,n0,n1,n2) NCDHW of in_dtype,
+ * outputs (batch,3,n0-96,n1-96,n2-96) NCDHW of out_dtype.  vel_dev / vel_fac must be
+ * non-NULL iff the parameters were set with compute_vel.  Weights come from the last
+ * nbe_modulate (its batch must equal `batch`, or 1 = shared).  Asynchronous on `stream`. */
+int nbe_forward(nbe_ctx* ctx, const void* x_dev, int in_dtype, int batch, const int32_t dims[3],
+                const float* Dz, const float* vel_fac, void* disp_dev, void* vel_dev, int out_dtype,
+                void* stream);
+
+/* SubboxProcessor.process_box (subbox.py:139-219) on HOST buffers for subboxes
+ * [sub_first, sub_first+sub_count): uploads the input box (3,size) once, gathers each
+ * periodic padded crop on the GPU with the reference's integer tables
+ * (SubboxConfig._get_crop_inds, subbox.py:81-97; `crop_idx`/`add_idx` below are those tables,
+ * computed by the caller), runs the net, pastes into a device slab and copies the finished
+ * slab back into disp_host / vel_host (3,size) of out_dtype.  Only the output voxels owned
+ * by the given subboxes are written.  Synchronous.
+ * crop_idx: int32 [n_sub_total][3][pad_len] with pad_len_d = crop_d + pad_lo_d + pad_hi_d
+ *           stored as three consecutive arrays per subbox (lengths plen[0..2]);
+ * add_idx0: int32 [n_sub_total][3] first output index per dim (add indices are contiguous,
+ *           tests/test_subbox.py:167-180).                                               */
+int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32_t size[3],
+                    const int32_t crop[3], const int32_t plen[3], const int32_t* crop_idx,
+                    const int32_t* add_idx0, int sub_first, int sub_count, float Dz, float vel_fac,
+                    void* disp_host, void* vel_host, int out_dtype);
+
+/* Bytes of device memory the context needs for one (n0,n1,n2) sample (activation arena). */
+size_t nbe_workspace_bytes(nbe_ctx* ctx, const int32_t dims[3]);
+
+/* Instrumentation: kernels launched by this context since the last reset, and per-launch
+ * device timings (CUDA events on the launching stream) of the most recent nbe_forward of
+ * sample 0 when profiling is enabled.  names/ms/flops arrays hold up to `cap` entries;
+ * returns the number of launches recorded.                                               */
+int64_t nbe_launch_count(nbe_ctx* ctx, int reset);
+int nbe_set_profiling(nbe_ctx* ctx, int enable);
+int nbe_get_profile(nbe_ctx* ctx, int cap, const char** names, float* ms, double* flops);
+
+/* Debug aid: read back activation tensor `act` (internal id, NDHWC fp16; which: 0 hi, 1 lo,
+ * 2 tangent) of the most recent plan.  host == NULL queries the size.                     */
+long long nbe_debug_read_act(nbe_ctx* ctx, int act, int which, void* host, size_t cap, int32_t shape_out[4]);
+
+/* Hardware self-test of the tcgen05 / TMA building blocks (descriptor encodings, swizzle
+ * modes, row-shifted operand starts).  Writes a human-readable report; returns 0 if the
+ * mandatory checks pass.                                                                 */
+int nbe_selftest(nbe_ctx* ctx, char* report, size_t report_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBE_H_ */

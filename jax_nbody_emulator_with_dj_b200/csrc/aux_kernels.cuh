@@ -1,0 +1,178 @@
+// HBM-bound helper kernels: fused weight modulation / demodulation / Dz-tangent / operand
+// packing, and the periodic gather + scale + channel-pack of the input subbox.
+#pragma once
+#include "conv_mma.cuh"
+
+namespace nbe {
+
+// ---------------------------------------------------------------------------------------
+// Weight modulation  (style_layers_vel.py:62-105; nbody_emulator.py:131-148, :189-219)
+//
+//   m_i   = s0*SW[i,0] + s1*SW[i,1] + sb[i]            w = W*m        dws = W*SW[i,1]
+//   n_o   = sqrt(sum_{i,t} w^2 + eps)                  dn_o = -sum(w*dws)/n^3
+//   Wn    = w/n                                        dWn  = dws/n + w*dn  (+ Wn/Dz on the
+//                                                      layers fed by the raw Dz-scaled field)
+//
+// One block per (layer, output channel, sample).  Results are written twice: fp32 OIDHW
+// (for nbe_get_modulated) and as fp16 tensor-core operand rows (hi, lo = fp16(Wn - hi), and
+// tangent), placed by per-layer emit rules into the B tensors of the conv launches.
+// ---------------------------------------------------------------------------------------
+enum { EMIT_WH = 0, EMIT_WL = 1, EMIT_DW = 2 };
+
+struct EmitRule {
+  int8_t what;        // EMIT_*
+  int8_t kind;        // tile-kind offset (x kind_stride tiles)
+  int16_t row_base;   // row of output channel 0 inside the B stage
+  int16_t kcol;       // column offset (16-channel rows only)
+  int16_t pad_;
+};
+
+struct LayerMeta {
+  const float* W;        // (cout, cin, k3) raw weight, or premodulated weight
+  const float* dW;       // premodulated dweight or nullptr
+  const float* SW;       // (cin, 2) or nullptr
+  const float* sb;       // (cin)
+  float* w32;            // [B][cout*cin*k3] modulated fp32 out
+  float* dw32;           // idem (vel) or nullptr
+  __half* dst;           // packed operand buffer of the owning launch (sample 0)
+  long long dst_sample_stride;   // halves between samples
+  int cout, cin, k3;
+  int first;             // add Wn/Dz to the tangent
+  int premod;
+  int vel;
+  int kc16;              // destination rows are 16 channels wide
+  int nrs;               // rows per B stage
+  int kc_stride, kind_stride;    // tiles
+  int n_rules;
+  int row0;              // first block index (prefix sum of cout)
+  int tap_tile[27];
+  EmitRule rules[6];
+};
+
+__global__ void __launch_bounds__(128)
+modulate_kernel(const LayerMeta* __restrict__ metas, int n_layers, const float* __restrict__ s0a,
+                const float* __restrict__ s1a, float eps) {
+  __shared__ float red1[4], red2[4];
+  __shared__ int s_layer;
+  if (threadIdx.x == 0) {
+    int l = 0;
+    while (l + 1 < n_layers && metas[l + 1].row0 <= static_cast<int>(blockIdx.x)) ++l;
+    s_layer = l;
+  }
+  __syncthreads();
+  const LayerMeta& M = metas[s_layer];
+  const int o = blockIdx.x - M.row0;
+  const int b = blockIdx.y;
+  const int ne = M.cin * M.k3;
+  const float s0 = s0a[b], s1 = s1a[b];
+  const float* Wrow = M.W + static_cast<long long>(o) * ne;
+
+  float inv_n = 1.f, dn = 0.f;
+  if (!M.premod) {
+    float a1 = 0.f, a2 = 0.f;
+    for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+      const int i = e / M.k3;
+      const float m = s0 * M.SW[2 * i] + s1 * M.SW[2 * i + 1] + M.sb[i];
+      const float w = Wrow[e] * m;
+      const float dws = Wrow[e] * M.SW[2 * i + 1];
+      a1 += w * w;
+      a2 += w * dws;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+      a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+    }
+    if ((threadIdx.x & 31) == 0) { red1[threadIdx.x >> 5] = a1; red2[threadIdx.x >> 5] = a2; }
+    __syncthreads();
+    a1 = red1[0] + red1[1] + red1[2] + red1[3];
+    a2 = red2[0] + red2[1] + red2[2] + red2[3];
+    const float n = sqrtf(a1 + eps);
+    inv_n = 1.f / n;
+    dn = -a2 / (n * n * n);
+  }
+  const float inv_Dz = 1.f / (s1 + 1.f);
+  const long long sample_off = static_cast<long long>(b) * M.dst_sample_stride;
+  const int rowlen = M.kc16 ? 16 : 64;
+  for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+    const int i = e / M.k3;
+    const int tap = e - i * M.k3;
+    float wn, dwn = 0.f;
+    if (M.premod) {
+      wn = Wrow[e];
+      if (M.vel) dwn = M.dW[static_cast<long long>(o) * ne + e];
+    } else {
+      const float m = s0 * M.SW[2 * i] + s1 * M.SW[2 * i + 1] + M.sb[i];
+      const float w = Wrow[e] * m;
+      wn = w * inv_n;
+      if (M.vel) {
+        const float dws = Wrow[e] * M.SW[2 * i + 1];
+        dwn = dws * inv_n + w * dn;
+        if (M.first) dwn += wn * inv_Dz;
+      }
+    }
+    const long long oidx = static_cast<long long>(b) * M.cout * ne + static_cast<long long>(o) * ne + e;
+    M.w32[oidx] = wn;
+    if (M.dw32) M.dw32[oidx] = dwn;
+    const __half wh = __float2half_rn(wn);
+    const __half wl = __float2half_rn(wn - __half2float(wh));
+    const __half dh = __float2half_rn(dwn);
+    const int kc = M.kc16 ? 0 : (i >> 6);
+    for (int r = 0; r < M.n_rules; ++r) {
+      const EmitRule R = M.rules[r];
+      const __half v = R.what == EMIT_WH ? wh : (R.what == EMIT_WL ? wl : dh);
+      const long long tile = M.tap_tile[tap] + kc * M.kc_stride + R.kind * M.kind_stride;
+      const int col = M.kc16 ? (R.kcol + i) : (i & 63);
+      M.dst[sample_off + (tile * M.nrs + R.row_base + o) * rowlen + col] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Input pack: periodic gather of the padded subbox with the reference's integer tables
+// (subbox.py:81-97), scale by Dz/6 (style_nbody_emulator_vel_core.py:132-134), split into
+// fp16 hi/lo and write 16-channel NDHWC records
+//     [xh0 xh1 xh2 | xl0 xl1 xl2 | xh0 xh1 xh2 | 0 x 7]
+// so that a single K=16 MMA against rows [Wh | Wh | Wl | 0] yields the 3-product primal.
+// ---------------------------------------------------------------------------------------
+struct PackArgs {
+  const void* src;
+  int32_t src_dtype;
+  int64_t src_sc, src_sd, src_sh;
+  const int32_t* idx_d;
+  const int32_t* idx_h;
+  const int32_t* idx_w;
+  int32_t n0, n1, n2;
+  float in_norm;
+  __half* out;
+};
+
+__global__ void __launch_bounds__(256) pack_input_kernel(const PackArgs a) {
+  const int64_t nvox = static_cast<int64_t>(a.n0) * a.n1 * a.n2;
+  for (int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; v < nvox;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(v % a.n2);
+    const int64_t t = v / a.n2;
+    const int h = static_cast<int>(t % a.n1);
+    const int d = static_cast<int>(t / a.n1);
+    const int64_t sidx = static_cast<int64_t>(a.idx_d[d]) * a.src_sd + static_cast<int64_t>(a.idx_h[h]) * a.src_sh +
+                         a.idx_w[w];
+    __half xh[3], xl[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float x;
+      if (a.src_dtype == 0) x = reinterpret_cast<const float*>(a.src)[sidx + c * a.src_sc];
+      else if (a.src_dtype == 1) x = __half2float(reinterpret_cast<const __half*>(a.src)[sidx + c * a.src_sc]);
+      else x = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.src)[sidx + c * a.src_sc]);
+      x = scale_in_dtype(x, a.in_norm, a.src_dtype);
+      xh[c] = __float2half_rn(x);
+      xl[c] = __float2half_rn(x - __half2float(xh[c]));
+    }
+    const __half z = __float2half_rn(0.f);
+    __half rec[16] = {xh[0], xh[1], xh[2], xl[0], xl[1], xl[2], xh[0], xh[1], xh[2], z, z, z, z, z, z, z};
+    uint4* dst = reinterpret_cast<uint4*>(a.out + v * 16);
+    dst[0] = *reinterpret_cast<const uint4*>(&rec[0]);
+    dst[1] = *reinterpret_cast<const uint4*>(&rec[8]);
+  }
+}
+
+}  // namespace nbe

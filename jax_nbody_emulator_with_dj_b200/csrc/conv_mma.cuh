@@ -1,0 +1,375 @@
+// Implicit-GEMM 3D convolution for sm_100a: TMA-fed tcgen05.mma with fp32 accumulators in
+// TMEM, warp-specialised (A-producer / B-producer / MMA issuer / 4 epilogue warps),
+// persistent over output tiles.
+//
+//   GEMM view:  M = output voxels (tile 8w x 16h, TM tiles stacked in h per work item),
+//               N = output channels of [y | dy],  K = taps x input channels.
+//
+// One launch evaluates a *sum of conv terms* ("groups") into the same accumulators: the
+// 27 taps of a 3^3 conv, the K-chunks of 128-channel inputs (un-materialised concat), the
+// folded 1^3 skip conv of a ResNet block (style_blocks_vel.py:112-159), the Dz-tangent
+// terms x*dW + dx*W (style_layers_vel.py:129-141) and, in split precision, the hi/lo
+// products.  A group loads one halo'd activation block {C, 8w, 16*TM+2 h, 1 d} per operand
+// with a single TMA box; its up-to-3 `kh` taps are served from that block by advancing the
+// UMMA descriptor start address by whole 8-row swizzle atoms (1024 B), so every activation
+// byte is fetched once per (kd,kw) instead of once per tap.
+//
+// Epilogue (fused): + bias, LeakyReLU with the tangent rule dy = y>0 ? dy : 0.01 dy
+// (layers_vel.py:178-186), fp16 hi (+lo) / tangent stores in NDHWC; or, for the last layer,
+// the model tail  disp = (net + x0)*6, vel = dnet*6vf + x0*6vf/Dz
+// (style_nbody_emulator_vel_core.py:187-193) written as NCDHW into the caller's box.
+#pragma once
+#include "ptx.cuh"
+
+namespace nbe {
+
+constexpr int kMaxGroups = 64;
+constexpr int kMaxAMaps = 32;
+constexpr int kConvThreads = 256;
+constexpr int kSmemLimit = 227 * 1024;
+
+struct MmaOp {
+  uint8_t a;        // A operand block of the group (0/1)
+  uint8_t n8;       // N / 8
+  uint16_t b_row;   // first row of the B stage (multiple of 8)
+  uint16_t d_col;   // first accumulator column
+  uint16_t pad_;
+};
+
+struct GroupDesc {
+  int16_t a_map[2];   // tensor-map index of operand 0 / 1 (-1: absent)
+  int8_t n_a;         // operand blocks to load (1 or 2)
+  int8_t ntaps;       // taps along h served from the block (1 or 3)
+  int8_t kc16;        // 1: 16-channel rows (32 B, SWIZZLE_32B); 0: 64-channel rows (128 B)
+  int8_t n_ops;
+  int16_t c0;         // channel coordinate of the box
+  int8_t dw, dh, dd;  // block origin relative to the tile origin
+  int8_t pad_;
+  int32_t brow0;      // B row of tap 0
+  int32_t brow_step;  // B rows between consecutive taps
+  MmaOp ops[3];
+};
+
+struct alignas(128) ConvLaunch {
+  CUtensorMap amap[kMaxAMaps];
+  CUtensorMap bmap64;
+  CUtensorMap bmap16;
+  GroupDesc groups[kMaxGroups];
+  int32_t n_groups;
+  int32_t n_par;            // 1, or 8 for the x2 up-sampling conv (one parity per item)
+  int32_t par_brow_step;    // B rows between parities
+  int32_t out_w, out_h, out_d;         // extent of the tile space
+  int64_t out_sw, out_sh, out_sd;      // output strides (elements) in tile space
+  int64_t par_ow, par_oh, par_od;      // output offsets (elements) of parity bits c, b, a
+  __half* out_h_ptr;        // primal hi  [.., cout_stride]
+  __half* out_l_ptr;        // primal lo or nullptr
+  __half* out_d_ptr;        // tangent or nullptr
+  const float* bias;        // [cout]
+  int32_t cout;             // output channels (primal)
+  int32_t vel;              // accumulator holds [y | dy]
+  int32_t act;              // LeakyReLU
+  int32_t pad_;
+};
+
+// Per-call arguments of the last layer's fused model tail.
+struct FinalArgs {
+  const void* src;          // raw input box (3, S0, S1, S2), in_dtype
+  int32_t src_dtype;
+  int64_t src_sc, src_sd, src_sh;      // element strides (w contiguous)
+  const int32_t* idx_d;     // gather tables of the centre crop (already offset by the pad)
+  const int32_t* idx_h;
+  const int32_t* idx_w;
+  void* disp;               // (3, ...) out_dtype, base at the paste anchor
+  void* vel;                // or nullptr
+  int32_t out_dtype;
+  int32_t mid_dtype;        // compute dtype of the model: results are rounded to it first
+  int64_t o_sc, o_sd, o_sh;
+  float in_norm;            // Dz/6
+  float six;                // 6
+  float dx_norm;            // 6*vel_fac
+  float x0_norm;            // 6*vel_fac/Dz
+};
+
+__device__ __forceinline__ float load_as_f32(const void* p, int64_t i, int dtype) {
+  if (dtype == 0) return reinterpret_cast<const float*>(p)[i];
+  if (dtype == 1) return __half2float(reinterpret_cast<const __half*>(p)[i]);
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ float round_to_dtype(float v, int dtype) {
+  if (dtype == 1) return __half2float(__float2half_rn(v));
+  if (dtype == 2) return __bfloat162float(__float2bfloat16_rn(v));
+  return v;
+}
+// x * (Dz/6) as the reference computes it, i.e. in the compute dtype with one rounding
+// (style_nbody_emulator_vel_core.py:132-134).
+__device__ __forceinline__ float scale_in_dtype(float x, float in_norm, int dtype) {
+  return round_to_dtype(x * round_to_dtype(in_norm, dtype), dtype);
+}
+__device__ __forceinline__ void store_from_f32(void* p, int64_t i, int dtype, float v) {
+  if (dtype == 0) reinterpret_cast<float*>(p)[i] = v;
+  else if (dtype == 1) reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+  else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+template <int NRS, int DC, int TM>
+struct ConvCfg {
+  static constexpr int kRows = (16 * TM + 2) * 8;          // rows of one activation block
+  static constexpr int kABlk = kRows * 128;                // bytes (64-channel rows)
+  static constexpr int kAStage = 2 * kABlk;
+  static constexpr int kBStage = NRS * 128;
+  static constexpr int kNA = (TM == 1) ? 3 : 2;
+  static constexpr int kBudget = kSmemLimit - 1024 /*align*/ - 1024 /*barriers+bias*/ - kNA * kAStage;
+  static constexpr int kNBraw = kBudget / kBStage;
+  static constexpr int kNB = kNBraw > 6 ? 6 : kNBraw;
+  static constexpr int kNBuf = (2 * TM * DC <= 512) ? 2 : 1;
+  static constexpr int kColsRaw = kNBuf * TM * DC;
+  static constexpr int kTmemCols = kColsRaw <= 32 ? 32 : kColsRaw <= 64 ? 64 : kColsRaw <= 128 ? 128
+                                   : kColsRaw <= 256 ? 256 : 512;
+  static constexpr int kSmemBytes = 1024 + kNA * kAStage + kNB * kBStage + 1024;
+  static_assert(kNB >= 2, "not enough shared memory for the B ring");
+  static_assert(kColsRaw <= 512, "TMEM overflow");
+};
+
+template <int NRS, int DC, int TM, bool FINAL>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_mma_kernel(const ConvLaunch* __restrict__ L, const FinalArgs fa) {
+  using Cfg = ConvCfg<NRS, DC, TM>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = a_smem + Cfg::kNA * Cfg::kAStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + Cfg::kNB * Cfg::kBStage);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + Cfg::kNA;
+  uint64_t* b_full = a_empty + Cfg::kNA;
+  uint64_t* b_empty = b_full + Cfg::kNB;
+  uint64_t* acc_full = b_empty + Cfg::kNB;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);   // up to 128 floats
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int n_groups = L->n_groups;
+  const int out_w = L->out_w, out_h = L->out_h, out_d = L->out_d;
+  const int tiles_w = (out_w + 7) >> 3;
+  const int tiles_h = (out_h + 16 * TM - 1) / (16 * TM);
+  const int n_par = L->n_par;
+  const long long n_items = 1ll * n_par * out_d * tiles_h * tiles_w;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::kNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < Cfg::kNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 3) {
+    const int nb = FINAL ? 16 : L->cout;
+    for (int i = lane; i < nb; i += 32) bias_s[i] = L->bias[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](long long item, int& par, int& w0, int& h0, int& d0) {
+    const int tw = static_cast<int>(item % tiles_w); item /= tiles_w;
+    const int th = static_cast<int>(item % tiles_h); item /= tiles_h;
+    d0 = static_cast<int>(item % out_d);
+    par = static_cast<int>(item / out_d);
+    w0 = tw * 8;
+    h0 = th * 16 * TM;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------ A producer (activation blocks)
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int par, w0, h0, d0;
+        decode(item, par, w0, h0, d0);
+        for (int g = 0; g < n_groups; ++g) {
+          const GroupDesc& G = L->groups[g];
+          const uint32_t blk = G.kc16 ? Cfg::kRows * 32 : Cfg::kABlk;
+          mbar_wait(&a_empty[s], ph ^ 1);
+          mbar_expect_tx(&a_full[s], blk * G.n_a);
+          for (int q = 0; q < G.n_a; ++q)
+            tma_load_4d(a_smem + s * Cfg::kAStage + q * Cfg::kABlk, &L->amap[G.a_map[q]], &a_full[s],
+                        G.c0, w0 + G.dw, h0 + G.dh, d0 + G.dd);
+          if (++s == Cfg::kNA) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ B producer (weight tiles)
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int par, w0, h0, d0;
+        decode(item, par, w0, h0, d0);
+        for (int g = 0; g < n_groups; ++g) {
+          const GroupDesc& G = L->groups[g];
+          const CUtensorMap* bm = G.kc16 ? &L->bmap16 : &L->bmap64;
+          const uint32_t bytes = G.kc16 ? NRS * 32 : NRS * 128;
+          const int row0 = G.brow0 + par * L->par_brow_step;
+          for (int j = 0; j < G.ntaps; ++j) {
+            mbar_wait(&b_empty[s], ph ^ 1);
+            mbar_expect_tx(&b_full[s], bytes);
+            tma_load_2d(b_smem + s * Cfg::kBStage, bm, &b_full[s], 0, row0 + j * G.brow_step);
+            if (++s == Cfg::kNB) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc_base = umma_idesc_f16(128, 0, false);
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, buf = 0, pacc = 0;
+      for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        mbar_wait(&acc_empty[buf], pacc ^ 1);
+        tc_fence_after();
+        for (int g = 0; g < n_groups; ++g) {
+          const GroupDesc& G = L->groups[g];
+          const uint32_t rowb = G.kc16 ? 32u : 128u;
+          const uint32_t sbo = rowb * 8u;
+          const uint64_t lay = G.kc16 ? UMMA_SW32 : UMMA_SW128;
+          const int ksteps = G.kc16 ? 1 : 4;
+          mbar_wait(&a_full[sa], pa);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(a_smem + sa * Cfg::kAStage);
+          for (int j = 0; j < G.ntaps; ++j) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(b_smem + sb * Cfg::kBStage);
+#pragma unroll
+            for (int t = 0; t < TM; ++t) {
+              const uint32_t d_tile = tmem_base + (buf * TM + t) * DC;
+              const uint32_t a_row = static_cast<uint32_t>(t * 16 + j) * sbo;
+              for (int k = 0; k < ksteps; ++k) {
+                for (int o = 0; o < G.n_ops; ++o) {
+                  const MmaOp op = G.ops[o];
+                  const uint64_t ad = umma_smem_desc(a_base + op.a * Cfg::kABlk + a_row + k * 32, sbo, lay);
+                  const uint64_t bd = umma_smem_desc(b_base + op.b_row * rowb + k * 32, sbo, lay);
+                  const uint32_t acc = (g | j | k | o) != 0 ? 1u : 0u;
+                  umma_f16(d_tile + op.d_col, ad, bd, idesc_base | (static_cast<uint32_t>(op.n8) << 17), acc);
+                }
+              }
+            }
+            umma_commit(&b_empty[sb]);
+            if (++sb == Cfg::kNB) { sb = 0; pb ^= 1; }
+          }
+          umma_commit(&a_empty[sa]);
+          if (++sa == Cfg::kNA) { sa = 0; pa ^= 1; }
+        }
+        umma_commit(&acc_full[buf]);
+        if (++buf == Cfg::kNBuf) { buf = 0; pacc ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ epilogue (128 threads, thread <-> row)
+    const int q = warp & 3;                       // TMEM lane quarter of this warp
+    const int r = q * 32 + lane;                  // accumulator row
+    uint32_t buf = 0, pacc = 0;
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int par, w0, h0, d0;
+      decode(item, par, w0, h0, d0);
+      mbar_wait(&acc_full[buf], pacc);
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < TM; ++t) {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (buf * TM + t) * DC;
+        const int w = w0 + (r & 7);
+        const int h = h0 + t * 16 + (r >> 3);
+        const bool valid = (w < out_w) && (h < out_h);
+        if constexpr (FINAL) {
+          uint32_t v[16];
+          tmem_ld16(taddr, v);
+          tmem_ld_wait();
+          if (valid) {
+            const int64_t sidx = static_cast<int64_t>(fa.idx_d[d0]) * fa.src_sd +
+                                 static_cast<int64_t>(fa.idx_h[h]) * fa.src_sh + fa.idx_w[w];
+            const int64_t oidx = static_cast<int64_t>(d0) * fa.o_sd + static_cast<int64_t>(h) * fa.o_sh + w;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float x0 = scale_in_dtype(load_as_f32(fa.src, sidx + c * fa.src_sc, fa.src_dtype),
+                                              fa.in_norm, fa.src_dtype);
+              float net = __uint_as_float(v[c]) + bias_s[c];
+              if (fa.vel != nullptr) {
+                const float dnet = __uint_as_float(v[8 + c]);
+                store_from_f32(fa.vel, oidx + c * fa.o_sc, fa.out_dtype,
+                               round_to_dtype(dnet * fa.dx_norm + x0 * fa.x0_norm, fa.mid_dtype));
+              } else {
+                net += __uint_as_float(v[8 + c]);     // displacement-only: columns 8..10 hold xh*Wl
+              }
+              store_from_f32(fa.disp, oidx + c * fa.o_sc, fa.out_dtype,
+                             round_to_dtype((net + x0) * fa.six, fa.mid_dtype));
+            }
+          }
+        } else {
+          const int cout = L->cout;
+          const bool vel = L->vel != 0;
+          const bool act = L->act != 0;
+          const int pc = par & 1, pb2 = (par >> 1) & 1, pa2 = (par >> 2) & 1;
+          const int64_t voff = static_cast<int64_t>(d0) * L->out_sd + static_cast<int64_t>(h) * L->out_sh +
+                               static_cast<int64_t>(w) * L->out_sw + pc * L->par_ow + pb2 * L->par_oh +
+                               pa2 * L->par_od;
+          __half* oh = L->out_h_ptr + voff;
+          __half* ol = L->out_l_ptr ? L->out_l_ptr + voff : nullptr;
+          __half* od = L->out_d_ptr ? L->out_d_ptr + voff : nullptr;
+          for (int c = 0; c < cout; c += 32) {
+            uint32_t y[32], dy[32];
+            tmem_ld32(taddr + c, y);
+            if (vel) tmem_ld32(taddr + cout + c, dy);
+            tmem_ld_wait();
+            uint32_t ph[16], pl[16], pd[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float y0 = __uint_as_float(y[i]) + bias_s[c + i];
+              float y1 = __uint_as_float(y[i + 1]) + bias_s[c + i + 1];
+              float d0v = vel ? __uint_as_float(dy[i]) : 0.f;
+              float d1v = vel ? __uint_as_float(dy[i + 1]) : 0.f;
+              if (act) {
+                d0v = y0 > 0.f ? d0v : 0.01f * d0v;
+                d1v = y1 > 0.f ? d1v : 0.01f * d1v;
+                y0 = y0 >= 0.f ? y0 : 0.01f * y0;
+                y1 = y1 >= 0.f ? y1 : 0.01f * y1;
+              }
+              const __half2 hh = __floats2half2_rn(y0, y1);
+              const float2 hf = __half22float2(hh);
+              const __half2 ll = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+              const __half2 dd = __floats2half2_rn(d0v, d1v);
+              ph[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+              pl[i >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
+              pd[i >> 1] = *reinterpret_cast<const uint32_t*>(&dd);
+            }
+            if (valid) {
+#pragma unroll
+              for (int v4 = 0; v4 < 4; ++v4) {
+                st_global_v4(oh + c + v4 * 8, make_uint4(ph[4 * v4], ph[4 * v4 + 1], ph[4 * v4 + 2], ph[4 * v4 + 3]));
+                if (ol) st_global_v4(ol + c + v4 * 8, make_uint4(pl[4 * v4], pl[4 * v4 + 1], pl[4 * v4 + 2], pl[4 * v4 + 3]));
+                if (od) st_global_v4(od + c + v4 * 8, make_uint4(pd[4 * v4], pd[4 * v4 + 1], pd[4 * v4 + 2], pd[4 * v4 + 3]));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[buf]);
+      if (++buf == Cfg::kNBuf) { buf = 0; pacc ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace nbe

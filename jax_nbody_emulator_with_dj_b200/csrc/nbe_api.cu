@@ -1,0 +1,1002 @@
+// libnbe_b200: C ABI (include/nbe.h) over the sm_100a kernels.  Host side: parameter upload,
+// static description of the 15-block V-Net as 27 fused conv launches, tensor-core operand
+// layout of the weights, per-shape plans (activation arena + TMA tensor maps) and the
+// subbox loop with host<->device staging.
+#include "../../include/nbe.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "conv_mma.cuh"
+
+using namespace nbe;
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+enum ConvType { T_CONV3 = 0, T_SKIP1 = 1, T_DOWN = 2, T_UP = 3 };
+enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_COUNT };
+struct InstInfo { int nrs, dc, tm; bool fin; };
+const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32, 16, 2, true},
+                                 {128, 64, 2, false},  {64, 64, 2, false},   {256, 128, 2, false}};
+
+// activation tensors of the net
+enum ActId {
+  A_IN16 = 0, A_L00_0, A_L00, A_L01_0, A_Y0, A_D0, A_L1_0, A_Y1, A_D1, A_L2_0, A_Y2, A_D2, A_C_0, A_C,
+  A_U2, A_R2_0, A_R2, A_U1, A_R1_0, A_R1, A_U0, A_R00_0, A_R00, A_R01_0, A_OUT, A_COUNT
+};
+
+struct Src { int act; int crop; int c0; bool kc16; };
+struct ConvPart { int layer; int type; int off; std::vector<Src> src; int tile_base64 = 0, tile_base16 = 0; };
+struct StaticLaunch {
+  std::string name;
+  int inst;
+  std::vector<ConvPart> parts;
+  int in_ref;      // activation whose frame defines the tile space
+  int out_act;
+  int cout;
+  // per-sample packed weight regions (in halves, relative to the sample base)
+  long long b64_off = 0, b16_off = 0;
+  int n_tiles64 = 0, n_tiles16 = 0;
+  long long bias_off = 0;   // floats, in the bias buffer
+};
+
+struct ActBuf { int c = 0, d = 0, h = 0, w = 0; size_t off_hi = 0, off_lo = 0, off_dx = 0; };
+
+struct HostLaunch {
+  ConvLaunch L;
+  int inst;
+  int grid;
+  double flops;
+  std::string name;
+};
+
+struct Plan {
+  int dims[3];
+  int batch;
+  ActBuf act[A_COUNT];
+  size_t arena_bytes = 0;
+  std::vector<HostLaunch> launches;   // [sample][launch] flattened
+  int n_launch = 0;
+  ConvLaunch* dev_launches = nullptr;
+};
+
+struct Layer {
+  std::string block, layer;
+  int cout, cin, k;
+  float *W = nullptr, *dW = nullptr, *SW = nullptr, *sb = nullptr;   // device
+  std::vector<float> bias;
+  long long w32_off = 0;    // floats into w32 / dw32 per sample
+};
+
+}  // namespace
+
+struct nbe_ctx {
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+  EncodeTiledFn encode = nullptr;
+  cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+
+  bool have_params = false, premod = false, vel = true;
+  float eps = 1e-8f;
+  int precision = NBE_PREC_SPLIT;
+  std::vector<Layer> layers;
+  std::map<std::string, int> lidx;
+
+  // static launch list + weight layout
+  std::vector<StaticLaunch> sl;
+  std::vector<LayerMeta> metas;
+  long long packed_halves = 0;      // per sample
+  long long w32_floats = 0;         // per sample
+  LayerMeta* d_metas = nullptr;
+  float* d_bias = nullptr;
+  long long bias_floats = 0;
+
+  // modulation state
+  int mod_batch = 0;
+  __half* d_packed = nullptr; size_t packed_cap = 0;
+  float *d_w32 = nullptr, *d_dw32 = nullptr; size_t w32_cap = 0, dw32_cap = 0;
+  float *d_s0 = nullptr, *d_s1 = nullptr; int s_cap = 0;
+
+  // plans
+  std::vector<Plan*> plans;
+  uint8_t* arena = nullptr; size_t arena_cap = 0;
+  int32_t* d_ident = nullptr; int ident_cap = 0;     // identity gather table for nbe_forward
+
+  // process_box staging
+  void* d_box = nullptr; size_t box_cap = 0;
+  void* d_disp = nullptr; void* d_velo = nullptr; size_t out_cap = 0, velo_cap = 0;
+  int32_t* d_idx = nullptr; size_t idx_cap = 0;
+
+  // instrumentation
+  int64_t launches = 0;
+  bool profiling = false;
+  std::vector<std::string> prof_names;
+  std::vector<float> prof_ms;
+  std::vector<double> prof_flops;
+};
+
+namespace {
+
+int fail(nbe_ctx* c, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, NBE_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int ensure(nbe_ctx* ctx, void** p, size_t* cap, size_t need) {
+  if (*cap >= need && *p) return NBE_OK;
+  if (*p) { CK(cudaDeviceSynchronize()); CK(cudaFree(*p)); *p = nullptr; *cap = 0; }
+  CK(cudaMalloc(p, need));
+  *cap = need;
+  return NBE_OK;
+}
+
+int find_layer(nbe_ctx* ctx, const char* block, const char* layer) {
+  auto it = ctx->lidx.find(std::string(block) + "/" + layer);
+  return it == ctx->lidx.end() ? -1 : it->second;
+}
+
+// ----------------------------------------------------------------------------------------
+// static description of the net as fused launches (see DESIGN.md "launch list")
+// ----------------------------------------------------------------------------------------
+int build_static(nbe_ctx* ctx) {
+  const bool vel = ctx->vel;
+  const bool split = ctx->precision == NBE_PREC_SPLIT;
+  ctx->sl.clear();
+  auto L = [&](const char* b, const char* l) { return find_layer(ctx, b, l); };
+  auto inst64 = [&]() { return vel ? I_128_128_2 : (split ? I_128_64_2 : I_64_64_2); };
+  auto inst128 = [&]() { return vel ? I_256_256_1 : (split ? I_256_128_2 : I_128_128_2); };
+
+  auto add = [&](const std::string& name, int inst, int in_ref, int out_act, int cout,
+                 std::vector<ConvPart> parts) {
+    StaticLaunch s;
+    s.name = name; s.inst = inst; s.in_ref = in_ref; s.out_act = out_act; s.cout = cout; s.parts = parts;
+    ctx->sl.push_back(s);
+  };
+  auto res_block = [&](const char* blk, std::vector<Src> in, int in_ref, int mid_act, int out_act, int mid,
+                       bool fin) {
+    add(std::string(blk) + ".conv_0", mid == 128 ? inst128() : inst64(), in_ref, mid_act, mid,
+        {ConvPart{L(blk, "conv_0"), T_CONV3, 0, in}});
+    std::vector<Src> midsrc;
+    for (int q = 0; q < mid / 64; ++q) midsrc.push_back(Src{mid_act, 0, q * 64, false});
+    add(std::string(blk) + ".conv_1+skip", fin ? I_FINAL : inst64(), mid_act, out_act, fin ? 3 : 64,
+        {ConvPart{L(blk, "conv_1"), T_CONV3, 0, midsrc}, ConvPart{L(blk, "skip"), T_SKIP1, 2, in}});
+  };
+  auto S = [](int act, int crop = 0, int c0 = 0, bool kc16 = false) { return Src{act, crop, c0, kc16}; };
+
+  res_block("conv_l00", {S(A_IN16, 0, 0, true)}, A_IN16, A_L00_0, A_L00, 64, false);
+  res_block("conv_l01", {S(A_L00)}, A_L00, A_L01_0, A_Y0, 64, false);
+  add("down_l0", inst64(), A_D0, A_D0, 64, {ConvPart{L("down_l0", "conv_0"), T_DOWN, 0, {S(A_Y0)}}});
+  res_block("conv_l1", {S(A_D0)}, A_D0, A_L1_0, A_Y1, 64, false);
+  add("down_l1", inst64(), A_D1, A_D1, 64, {ConvPart{L("down_l1", "conv_0"), T_DOWN, 0, {S(A_Y1)}}});
+  res_block("conv_l2", {S(A_D1)}, A_D1, A_L2_0, A_Y2, 64, false);
+  add("down_l2", inst64(), A_D2, A_D2, 64, {ConvPart{L("down_l2", "conv_0"), T_DOWN, 0, {S(A_Y2)}}});
+  res_block("conv_c", {S(A_D2)}, A_D2, A_C_0, A_C, 64, false);
+  add("up_r2", inst64(), A_C, A_U2, 64, {ConvPart{L("up_r2", "conv_0"), T_UP, 0, {S(A_C)}}});
+  res_block("conv_r2", {S(A_Y2, 4), S(A_U2)}, A_U2, A_R2_0, A_R2, 128, false);
+  add("up_r1", inst64(), A_R2, A_U1, 64, {ConvPart{L("up_r1", "conv_0"), T_UP, 0, {S(A_R2)}}});
+  res_block("conv_r1", {S(A_Y1, 16), S(A_U1)}, A_U1, A_R1_0, A_R1, 128, false);
+  add("up_r0", inst64(), A_R1, A_U0, 64, {ConvPart{L("up_r0", "conv_0"), T_UP, 0, {S(A_R1)}}});
+  res_block("conv_r00", {S(A_Y0, 40), S(A_U0)}, A_U0, A_R00_0, A_R00, 128, false);
+  res_block("conv_r01", {S(A_R00)}, A_R00, A_R01_0, A_OUT, 64, true);
+
+  for (auto& s : ctx->sl)
+    for (auto& p : s.parts)
+      if (p.layer < 0) return fail(ctx, NBE_ERR_STATE, "layer missing for launch %s", s.name.c_str());
+
+  // ---- weight layout: tiles, emit rules, LayerMeta
+  const int nkind = (vel && split) ? 2 : 1;
+  ctx->metas.assign(ctx->layers.size(), LayerMeta{});
+  long long off = 0, boff = 0;
+  int row0 = 0;
+  for (size_t li = 0; li < ctx->layers.size(); ++li) {     // block order of the modulate grid
+    ctx->metas[li].row0 = row0;
+    row0 += ctx->layers[li].cout;
+  }
+  for (auto& s : ctx->sl) {
+    const InstInfo ii = kInst[s.inst];
+    int t64 = 0, t16 = 0;
+    for (auto& p : s.parts) {
+      const Layer& ly = ctx->layers[p.layer];
+      const bool k16 = p.src[0].kc16;
+      const int nkc = static_cast<int>(p.src.size());
+      const int nk = k16 ? 1 : nkind;
+      LayerMeta& M = ctx->metas[p.layer];
+      int& tb = k16 ? t16 : t64;
+      (k16 ? p.tile_base16 : p.tile_base64) = tb;
+      M.kc16 = k16; M.nrs = ii.nrs;
+      const int k3 = ly.k * ly.k * ly.k;
+      if (p.type == T_CONV3) {
+        for (int kd = 0; kd < 3; ++kd) for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw)
+          M.tap_tile[(kd * 3 + kh) * 3 + kw] = tb + ((kd * 3 + kw) * nkc * nk) * 3 + kh;
+        M.kc_stride = nk * 3; M.kind_stride = 3;
+        tb += 27 * nkc * nk;
+      } else if (p.type == T_SKIP1) {
+        M.tap_tile[0] = tb; M.kc_stride = nk; M.kind_stride = 1; tb += nkc * nk;
+      } else if (p.type == T_DOWN) {
+        for (int t = 0; t < 8; ++t) M.tap_tile[t] = tb + t * nkc * nk;
+        M.kc_stride = nk; M.kind_stride = 1; tb += 8 * nkc * nk;
+      } else {  // T_UP: parity p uses tap 7-p
+        for (int t = 0; t < 8; ++t) M.tap_tile[t] = tb + (7 - t) * nkc * nk;
+        M.kc_stride = nk; M.kind_stride = 1; tb += 8 * nkc * nk;
+      }
+      (void)k3;
+      // emit rules
+      int nr = 0;
+      auto rule = [&](int what, int kind, int row, int kcol) {
+        M.rules[nr].what = static_cast<int8_t>(what); M.rules[nr].kind = static_cast<int8_t>(kind);
+        M.rules[nr].row_base = static_cast<int16_t>(row); M.rules[nr].kcol = static_cast<int16_t>(kcol);
+        ++nr;
+      };
+      const int C = ly.cout;
+      if (ii.fin) {
+        if (vel) {
+          rule(EMIT_WH, 0, 0, 0); rule(EMIT_DW, 0, 8, 0); rule(EMIT_WH, 0, 24, 0);
+          if (split) { rule(EMIT_WL, 1, 0, 0); rule(EMIT_WH, 1, 16, 0); }
+        } else {
+          rule(EMIT_WH, 0, 0, 0);
+          if (split) { rule(EMIT_WL, 0, 8, 0); rule(EMIT_WH, 0, 16, 0); }
+        }
+      } else if (k16) {
+        rule(EMIT_WH, 0, 0, 0); rule(EMIT_WH, 0, 0, 3); rule(EMIT_WL, 0, 0, 6);
+        if (vel) rule(EMIT_DW, 0, C, 0);
+      } else if (vel) {
+        rule(EMIT_WH, 0, 0, 0); rule(EMIT_DW, 0, C, 0);
+        if (split) { rule(EMIT_WL, 1, 0, 0); rule(EMIT_WH, 1, C, 0); }
+      } else {
+        rule(EMIT_WH, 0, 0, 0);
+        if (split) rule(EMIT_WL, 0, C, 0);
+      }
+      M.n_rules = nr;
+    }
+    s.n_tiles64 = t64; s.n_tiles16 = t16;
+    s.b64_off = off; off += static_cast<long long>(t64) * ii.nrs * 64;
+    s.b16_off = off; off += static_cast<long long>(t16) * ii.nrs * 16;
+    off = static_cast<long long>(align_up(static_cast<size_t>(off), 512));
+    s.bias_off = boff; boff += 128;
+  }
+  ctx->packed_halves = off;
+  ctx->bias_floats = boff;
+  // per-layer fp32 output offsets and destination pointers are filled in at modulate time
+  long long w32 = 0;
+  for (auto& ly : ctx->layers) { ly.w32_off = w32; w32 += static_cast<long long>(ly.cout) * ly.cin * ly.k * ly.k * ly.k; }
+  ctx->w32_floats = w32;
+
+  // bias buffers (conv bias + folded skip bias), fp32
+  {
+    std::vector<float> hb(static_cast<size_t>(boff), 0.f);
+    for (auto& s : ctx->sl)
+      for (auto& p : s.parts) {
+        const Layer& ly = ctx->layers[p.layer];
+        for (int o = 0; o < ly.cout; ++o) hb[s.bias_off + o] += ly.bias[o];
+      }
+    if (ctx->d_bias) { cudaFree(ctx->d_bias); ctx->d_bias = nullptr; }
+    CK(cudaMalloc(&ctx->d_bias, hb.size() * sizeof(float)));
+    CK(cudaMemcpy(ctx->d_bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  // plans depend on the layout: drop them
+  for (auto* p : ctx->plans) { if (p->dev_launches) cudaFree(p->dev_launches); delete p; }
+  ctx->plans.clear();
+  ctx->mod_batch = 0;
+  return NBE_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// tensor maps
+// ----------------------------------------------------------------------------------------
+int make_act_map(nbe_ctx* ctx, CUtensorMap* m, const __half* base, int C, int W, int H, int D, int kc, int box_h,
+                 int par /* -1 or parity (a,b,c) of a stride-2 view */) {
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(D)};
+  cuuint64_t str[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(C) * W * 2,
+                       static_cast<cuuint64_t>(C) * W * H * 2};
+  const __half* p = base;
+  if (par >= 0) {
+    const int a = (par >> 2) & 1, b = (par >> 1) & 1, c = par & 1;
+    p = base + ((static_cast<size_t>(a) * H + b) * W + c) * C;
+    dims[1] = W / 2; dims[2] = H / 2; dims[3] = D / 2;
+    str[0] *= 2; str[1] *= 2; str[2] *= 2;
+  }
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(kc), 8u, static_cast<cuuint32_t>(box_h), 1u};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(p), dims, str, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, NBE_ERR_CUDA, "cuTensorMapEncodeTiled(act C=%d W=%d H=%d D=%d) -> %d", C, W, H, D, (int)r);
+  return NBE_OK;
+}
+
+int make_b_map(nbe_ctx* ctx, CUtensorMap* m, const __half* base, int kc, long long rows, int nrs) {
+  if (rows <= 0) { memset(m, 0, sizeof(*m)); return NBE_OK; }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(kc), static_cast<cuuint64_t>(rows)};
+  cuuint64_t str[1] = {static_cast<cuuint64_t>(kc) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kc), static_cast<cuuint32_t>(nrs)};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, str, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, NBE_ERR_CUDA, "cuTensorMapEncodeTiled(B kc=%d rows=%lld) -> %d", kc, rows, (int)r);
+  return NBE_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// per-shape plan
+// ----------------------------------------------------------------------------------------
+int chain(nbe_ctx* ctx, int n, int out[A_COUNT]) {
+  if (n % 8 != 0 || n < 104) return fail(ctx, NBE_ERR_ARG, "spatial size %d must be a multiple of 8 and >= 104", n);
+  out[A_IN16] = n; out[A_L00_0] = n - 2; out[A_L00] = n - 4; out[A_L01_0] = n - 6; out[A_Y0] = n - 8;
+  out[A_D0] = out[A_Y0] / 2; out[A_L1_0] = out[A_D0] - 2; out[A_Y1] = out[A_D0] - 4;
+  out[A_D1] = out[A_Y1] / 2; out[A_L2_0] = out[A_D1] - 2; out[A_Y2] = out[A_D1] - 4;
+  out[A_D2] = out[A_Y2] / 2; out[A_C_0] = out[A_D2] - 2; out[A_C] = out[A_D2] - 4;
+  out[A_U2] = 2 * out[A_C]; out[A_R2_0] = out[A_U2] - 2; out[A_R2] = out[A_U2] - 4;
+  out[A_U1] = 2 * out[A_R2]; out[A_R1_0] = out[A_U1] - 2; out[A_R1] = out[A_U1] - 4;
+  out[A_U0] = 2 * out[A_R1]; out[A_R00_0] = out[A_U0] - 2; out[A_R00] = out[A_U0] - 4;
+  out[A_R01_0] = out[A_R00] - 2; out[A_OUT] = out[A_R00] - 4;
+  if (out[A_Y2] - out[A_U2] != 8 || out[A_Y1] - out[A_U1] != 32 || out[A_Y0] - out[A_U0] != 80 || out[A_OUT] != n - 96)
+    return fail(ctx, NBE_ERR_ARG, "size %d does not produce consistent skip crops", n);
+  return NBE_OK;
+}
+
+int act_channels(int a) {
+  if (a == A_IN16) return 16;
+  if (a == A_R2_0 || a == A_R1_0 || a == A_R00_0) return 128;
+  if (a == A_OUT) return 0;
+  return 64;
+}
+
+int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
+  for (auto* p : ctx->plans)
+    if (p->dims[0] == dims[0] && p->dims[1] == dims[1] && p->dims[2] == dims[2] && p->batch == batch) { *out = p; return NBE_OK; }
+  const bool vel = ctx->vel;
+  const bool split = ctx->precision == NBE_PREC_SPLIT;
+  Plan* P = new Plan();
+  P->dims[0] = dims[0]; P->dims[1] = dims[1]; P->dims[2] = dims[2]; P->batch = batch;
+  int cd[A_COUNT], ch[A_COUNT], cw[A_COUNT];
+  int rc;
+  if ((rc = chain(ctx, dims[0], cd)) || (rc = chain(ctx, dims[1], ch)) || (rc = chain(ctx, dims[2], cw))) { delete P; return rc; }
+  size_t off = 0;
+  for (int a = 0; a < A_COUNT; ++a) {
+    ActBuf& B = P->act[a];
+    B.c = act_channels(a); B.d = cd[a]; B.h = ch[a]; B.w = cw[a];
+    if (a == A_OUT) continue;
+    const size_t bytes = align_up(static_cast<size_t>(B.c) * B.d * B.h * B.w * 2, 1024);
+    B.off_hi = off; off += bytes;
+    if (a != A_IN16) {
+      if (split) { B.off_lo = off; off += bytes; }
+      if (vel) { B.off_dx = off; off += bytes; }
+    }
+  }
+  P->arena_bytes = off;
+  if (ctx->arena_cap < off) {
+    rc = ensure(ctx, reinterpret_cast<void**>(&ctx->arena), &ctx->arena_cap, off);
+    if (rc) { delete P; return rc; }
+    // the arena moved: every cached plan holds stale pointers
+    for (auto* p : ctx->plans) { if (p->dev_launches) cudaFree(p->dev_launches); delete p; }
+    ctx->plans.clear();
+  }
+  uint8_t* arena = ctx->arena;
+  auto hi = [&](int a) { return reinterpret_cast<__half*>(arena + P->act[a].off_hi); };
+  auto lo = [&](int a) { return reinterpret_cast<__half*>(arena + P->act[a].off_lo); };
+  auto dx = [&](int a) { return reinterpret_cast<__half*>(arena + P->act[a].off_dx); };
+
+  const int nl = static_cast<int>(ctx->sl.size());
+  P->n_launch = nl;
+  P->launches.resize(static_cast<size_t>(nl) * batch);
+  for (int b = 0; b < batch; ++b) {
+    const int wb = (ctx->mod_batch == 1) ? 0 : b;       // shared weights when modulated for one sample
+    const __half* packed = ctx->d_packed + static_cast<size_t>(wb) * ctx->packed_halves;
+    for (int li = 0; li < nl; ++li) {
+      const StaticLaunch& s = ctx->sl[li];
+      const InstInfo ii = kInst[s.inst];
+      HostLaunch& H = P->launches[static_cast<size_t>(b) * nl + li];
+      H.inst = s.inst; H.name = s.name; H.flops = 0;
+      ConvLaunch& Lc = H.L;
+      memset(&Lc, 0, sizeof Lc);
+      const int box_h = 16 * ii.tm + 2;
+      std::map<std::pair<const void*, int>, int> amap;
+      int n_amap = 0;
+      auto get_map = [&](const __half* ptr, int act, int par) -> int {
+        auto key = std::make_pair(static_cast<const void*>(ptr), par);
+        auto it = amap.find(key);
+        if (it != amap.end()) return it->second;
+        if (n_amap >= kMaxAMaps) return -1;
+        const ActBuf& B = P->act[act];
+        if (make_act_map(ctx, &Lc.amap[n_amap], ptr, B.c, B.w, B.h, B.d, B.c == 16 ? 16 : 64, box_h, par)) return -1;
+        amap[key] = n_amap;
+        return n_amap++;
+      };
+      if ((rc = make_b_map(ctx, &Lc.bmap64, packed + s.b64_off, 64, static_cast<long long>(s.n_tiles64) * ii.nrs, ii.nrs)) ||
+          (rc = make_b_map(ctx, &Lc.bmap16, packed + s.b16_off, 16, static_cast<long long>(s.n_tiles16) * ii.nrs, ii.nrs))) { delete P; return rc; }
+
+      int ng = 0;
+      bool bad = false;
+      auto push = [&](const GroupDesc& G) { if (ng < kMaxGroups) Lc.groups[ng++] = G; else bad = true; };
+      const int nkind = (vel && split) ? 2 : 1;
+      const ActBuf& OB = P->act[s.out_act];
+      // tile space = output voxels, except for the up-sampling conv (input voxels)
+      bool is_up = false;
+      for (const auto& p : s.parts) {
+        const Layer& ly = ctx->layers[p.layer];
+        const int nkc = static_cast<int>(p.src.size());
+        const bool k16 = p.src[0].kc16;
+        const int nk = k16 ? 1 : nkind;
+        const int C = ly.cout;
+        const int tb = k16 ? p.tile_base16 : p.tile_base64;
+        auto fill_ops = [&](GroupDesc& G, int kind, const Src& sc, int par) {
+          const __half* ph = hi(sc.act);
+          if (k16) {
+            G.n_a = 1; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par)); G.a_map[1] = -1;
+            G.n_ops = 1;
+            G.ops[0] = MmaOp{0, static_cast<uint8_t>((vel ? 2 * C : C) / 8), 0, 0, 0};
+            return;
+          }
+          const __half* pl = split ? lo(sc.act) : nullptr;
+          const __half* pd = vel ? dx(sc.act) : nullptr;
+          if (ii.fin) {
+            if (vel) {
+              G.n_a = 2; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par));
+              G.a_map[1] = static_cast<int16_t>(get_map(kind == 0 ? pd : pl, sc.act, par));
+              G.n_ops = 2;
+              G.ops[0] = MmaOp{0, 2, 0, 0, 0};
+              G.ops[1] = MmaOp{1, 2, 16, 0, 0};
+            } else if (split) {
+              G.n_a = 2; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par));
+              G.a_map[1] = static_cast<int16_t>(get_map(pl, sc.act, par));
+              G.n_ops = 2;
+              G.ops[0] = MmaOp{0, 2, 0, 0, 0};
+              G.ops[1] = MmaOp{1, 2, 16, 0, 0};
+            } else {
+              G.n_a = 1; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par)); G.a_map[1] = -1;
+              G.n_ops = 1;
+              G.ops[0] = MmaOp{0, 2, 0, 0, 0};
+            }
+            return;
+          }
+          if (vel) {
+            G.n_a = 2; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par));
+            if (kind == 0) {         // [Wh | dW]:  D[0:2C] = xh*[Wh|dW];  D[C:2C] += dx*Wh
+              G.a_map[1] = static_cast<int16_t>(get_map(pd, sc.act, par));
+              G.n_ops = 2;
+              G.ops[0] = MmaOp{0, static_cast<uint8_t>(2 * C / 8), 0, 0, 0};
+              G.ops[1] = MmaOp{1, static_cast<uint8_t>(C / 8), 0, static_cast<uint16_t>(C), 0};
+            } else {                 // [Wl | Wh]:  D[0:C] += xh*Wl + xl*Wh
+              G.a_map[1] = static_cast<int16_t>(get_map(pl, sc.act, par));
+              G.n_ops = 2;
+              G.ops[0] = MmaOp{0, static_cast<uint8_t>(C / 8), 0, 0, 0};
+              G.ops[1] = MmaOp{1, static_cast<uint8_t>(C / 8), static_cast<uint16_t>(C), 0, 0};
+            }
+          } else if (split) {        // [Wh | Wl]:  D = xh*Wh + xh*Wl + xl*Wh
+            G.n_a = 2; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par));
+            G.a_map[1] = static_cast<int16_t>(get_map(pl, sc.act, par));
+            G.n_ops = 3;
+            G.ops[0] = MmaOp{0, static_cast<uint8_t>(C / 8), 0, 0, 0};
+            G.ops[1] = MmaOp{0, static_cast<uint8_t>(C / 8), static_cast<uint16_t>(C), 0, 0};
+            G.ops[2] = MmaOp{1, static_cast<uint8_t>(C / 8), 0, 0, 0};
+          } else {
+            G.n_a = 1; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par)); G.a_map[1] = -1;
+            G.n_ops = 1;
+            G.ops[0] = MmaOp{0, static_cast<uint8_t>(C / 8), 0, 0, 0};
+          }
+        };
+        auto mk = [&](const Src& sc, int par, int dw_, int dh_, int dd_, int ntaps, int tile0, int kind) {
+          GroupDesc G;
+          memset(&G, 0, sizeof G);
+          G.ntaps = static_cast<int8_t>(ntaps); G.kc16 = k16 ? 1 : 0; G.c0 = static_cast<int16_t>(sc.c0);
+          G.dw = static_cast<int8_t>(sc.crop + p.off + dw_); G.dh = static_cast<int8_t>(sc.crop + p.off + dh_);
+          G.dd = static_cast<int8_t>(sc.crop + p.off + dd_);
+          G.brow0 = tile0 * ii.nrs; G.brow_step = ii.nrs;
+          fill_ops(G, kind, sc, par);
+          if (G.a_map[0] < 0 || (G.n_a == 2 && G.a_map[1] < 0)) bad = true;
+          push(G);
+        };
+        const double m = vel ? ((k16 || false) ? 2.0 : 3.0) : 1.0;
+        double vout = static_cast<double>(OB.d) * OB.h * OB.w;
+        if (p.type == T_CONV3) {
+          for (int kd = 0; kd < 3; ++kd) for (int kw = 0; kw < 3; ++kw)
+            for (int q = 0; q < nkc; ++q) for (int kind = 0; kind < nk; ++kind)
+              mk(p.src[q], -1, kw, 0, kd, 3, tb + (((kd * 3 + kw) * nkc + q) * nk + kind) * 3, kind);
+          H.flops += 2.0 * ly.cout * ly.cin * 27 * vout * m;
+        } else if (p.type == T_SKIP1) {
+          for (int q = 0; q < nkc; ++q) for (int kind = 0; kind < nk; ++kind)
+            mk(p.src[q], -1, 0, 0, 0, 1, tb + q * nk + kind, kind);
+          H.flops += 2.0 * ly.cout * ly.cin * vout * m;
+        } else if (p.type == T_DOWN) {
+          for (int t = 0; t < 8; ++t) for (int q = 0; q < nkc; ++q) for (int kind = 0; kind < nk; ++kind)
+            mk(p.src[q], t, 0, 0, 0, 1, tb + (t * nkc + q) * nk + kind, kind);
+          H.flops += 2.0 * ly.cout * ly.cin * 8 * vout * m;
+        } else {
+          is_up = true;
+          for (int q = 0; q < nkc; ++q) for (int kind = 0; kind < nk; ++kind)
+            mk(p.src[q], -1, 0, 0, 0, 1, tb + q * nk + kind, kind);
+          Lc.par_brow_step = nkc * nk * ii.nrs;
+          H.flops += 2.0 * ly.cout * ly.cin * vout * m;
+        }
+      }
+      if (bad) { delete P; return fail(ctx, NBE_ERR_STATE, "launch %s: too many groups / tensor maps", s.name.c_str()); }
+      Lc.n_groups = ng;
+      Lc.cout = s.cout; Lc.vel = vel ? 1 : 0; Lc.act = 1;
+      Lc.bias = ctx->d_bias + s.bias_off;
+      if (!ii.fin) {
+        Lc.out_h_ptr = hi(s.out_act);
+        Lc.out_l_ptr = split ? lo(s.out_act) : nullptr;
+        Lc.out_d_ptr = vel ? dx(s.out_act) : nullptr;
+      }
+      const int64_t C = OB.c;
+      if (is_up) {
+        const ActBuf& IB = P->act[s.in_ref];
+        Lc.n_par = 8; Lc.out_w = IB.w; Lc.out_h = IB.h; Lc.out_d = IB.d;
+        Lc.out_sw = 2 * C; Lc.out_sh = 2 * C * OB.w; Lc.out_sd = 2 * C * OB.w * OB.h;
+        Lc.par_ow = C; Lc.par_oh = C * OB.w; Lc.par_od = C * OB.w * OB.h;
+      } else {
+        Lc.n_par = 1; Lc.out_w = OB.w; Lc.out_h = OB.h; Lc.out_d = OB.d;
+        Lc.out_sw = C; Lc.out_sh = C * OB.w; Lc.out_sd = C * OB.w * OB.h;
+      }
+      const long long tiles = 1ll * Lc.n_par * Lc.out_d * ((Lc.out_h + 16 * ii.tm - 1) / (16 * ii.tm)) * ((Lc.out_w + 7) / 8);
+      H.grid = static_cast<int>(std::min<long long>(tiles, ctx->num_sms));
+    }
+  }
+  // upload
+  {
+    std::vector<ConvLaunch> tmp(P->launches.size());
+    for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = P->launches[i].L;
+    cudaError_t e = cudaMalloc(&P->dev_launches, tmp.size() * sizeof(ConvLaunch));
+    if (e == cudaSuccess) e = cudaMemcpy(P->dev_launches, tmp.data(), tmp.size() * sizeof(ConvLaunch), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete P; return fail(ctx, NBE_ERR_CUDA, "plan upload: %s", cudaGetErrorString(e)); }
+  }
+  ctx->plans.push_back(P);
+  *out = P;
+  return NBE_OK;
+}
+
+template <int NRS, int DC, int TM, bool FIN>
+cudaError_t launch_inst(const ConvLaunch* dl, const FinalArgs& fa, int grid, cudaStream_t st) {
+  using Cfg = ConvCfg<NRS, DC, TM>;
+  static bool attr_set = false;
+  auto kern = conv_mma_kernel<NRS, DC, TM, FIN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(dl, fa);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv(int inst, const ConvLaunch* dl, const FinalArgs& fa, int grid, cudaStream_t st) {
+  switch (inst) {
+    case I_128_128_2: return launch_inst<128, 128, 2, false>(dl, fa, grid, st);
+    case I_256_256_1: return launch_inst<256, 256, 1, false>(dl, fa, grid, st);
+    case I_FINAL: return launch_inst<32, 16, 2, true>(dl, fa, grid, st);
+    case I_128_64_2: return launch_inst<128, 64, 2, false>(dl, fa, grid, st);
+    case I_64_64_2: return launch_inst<64, 64, 2, false>(dl, fa, grid, st);
+    case I_256_128_2: return launch_inst<256, 128, 2, false>(dl, fa, grid, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// one sample through the net: pack + 27 conv launches.  `pk` and `fa` describe where the
+// padded input comes from and where the (n-96)^3 outputs go.
+int run_sample(nbe_ctx* ctx, Plan* P, int sample, PackArgs pk, FinalArgs fa, cudaStream_t st) {
+  pk.out = reinterpret_cast<__half*>(ctx->arena + P->act[A_IN16].off_hi);
+  pk.n0 = P->dims[0]; pk.n1 = P->dims[1]; pk.n2 = P->dims[2];
+  const long long nvox = 1ll * pk.n0 * pk.n1 * pk.n2;
+  const int pgrid = static_cast<int>(std::min<long long>((nvox + 255) / 256, 148ll * 16));
+  const bool prof = ctx->profiling && sample == 0;
+  std::vector<cudaEvent_t> ev;
+  auto mark = [&]() { if (prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); } };
+  if (prof) { ctx->prof_names.clear(); ctx->prof_ms.clear(); ctx->prof_flops.clear(); }
+  mark();
+  pack_input_kernel<<<pgrid, 256, 0, st>>>(pk);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (prof) { ctx->prof_names.push_back("pack_input"); ctx->prof_flops.push_back(0.0); }
+  mark();
+  for (int li = 0; li < P->n_launch; ++li) {
+    const HostLaunch& H = P->launches[static_cast<size_t>(sample) * P->n_launch + li];
+    CK(launch_conv(H.inst, P->dev_launches + static_cast<size_t>(sample) * P->n_launch + li, fa, H.grid, st));
+    ctx->launches++;
+    if (prof) { ctx->prof_names.push_back(H.name); ctx->prof_flops.push_back(H.flops); }
+    mark();
+  }
+  if (prof) {
+    CK(cudaStreamSynchronize(st));
+    for (size_t i = 0; i + 1 < ev.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      ctx->prof_ms.push_back(ms);
+    }
+    for (auto e : ev) cudaEventDestroy(e);
+  }
+  return NBE_OK;
+}
+
+int ensure_ident(nbe_ctx* ctx, int n) {
+  if (ctx->ident_cap >= n) return NBE_OK;
+  if (ctx->d_ident) { CK(cudaDeviceSynchronize()); CK(cudaFree(ctx->d_ident)); ctx->d_ident = nullptr; }
+  std::vector<int32_t> h(static_cast<size_t>(n));
+  for (int i = 0; i < n; ++i) h[i] = i;
+  CK(cudaMalloc(&ctx->d_ident, sizeof(int32_t) * n));
+  CK(cudaMemcpy(ctx->d_ident, h.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+  ctx->ident_cap = n;
+  return NBE_OK;
+}
+
+size_t dtype_size(int dt) { return dt == NBE_F32 ? 4 : 2; }
+
+}  // namespace
+
+// ========================================================================================
+// C ABI
+// ========================================================================================
+extern "C" {
+
+const char* nbe_version(void) { return "nbe_b200 0.1 (sm_100a, tcgen05/TMA)"; }
+
+int nbe_create(nbe_ctx** out, int device) {
+  if (!out) return NBE_ERR_ARG;
+  *out = nullptr;
+  nbe_ctx* ctx = new nbe_ctx();
+  ctx->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { delete ctx; return NBE_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return NBE_ERR_CUDA; }
+  if (prop.major != 10) { delete ctx; return NBE_ERR_UNSUPPORTED; }
+  ctx->num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+    delete ctx;
+    return NBE_ERR_CUDA;
+  }
+  ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  *out = ctx;
+  return NBE_OK;
+}
+
+void nbe_destroy(nbe_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto* p : ctx->plans) { if (p->dev_launches) cudaFree(p->dev_launches); delete p; }
+  for (auto& l : ctx->layers) { cudaFree(l.W); cudaFree(l.dW); cudaFree(l.SW); cudaFree(l.sb); }
+  cudaFree(ctx->d_metas); cudaFree(ctx->d_bias); cudaFree(ctx->d_packed); cudaFree(ctx->d_w32); cudaFree(ctx->d_dw32);
+  cudaFree(ctx->d_s0); cudaFree(ctx->d_s1); cudaFree(ctx->arena); cudaFree(ctx->d_ident); cudaFree(ctx->d_box);
+  cudaFree(ctx->d_disp); cudaFree(ctx->d_velo); cudaFree(ctx->d_idx);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+const char* nbe_last_error(const nbe_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int nbe_set_precision(nbe_ctx* ctx, int precision) {
+  if (!ctx) return NBE_ERR_ARG;
+  if (precision != NBE_PREC_SPLIT && precision != NBE_PREC_FP16) return fail(ctx, NBE_ERR_ARG, "unknown precision %d", precision);
+  CK(cudaSetDevice(ctx->device));
+  if (precision == ctx->precision) return NBE_OK;
+  ctx->precision = precision;
+  if (ctx->have_params) { CK(cudaDeviceSynchronize()); return build_static(ctx); }
+  return NBE_OK;
+}
+
+int nbe_set_params(nbe_ctx* ctx, const nbe_layer_params* layers, int n_layers, int premodulated, int compute_vel,
+                   float eps) {
+  if (!ctx || !layers) return NBE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  if (n_layers != 33) return fail(ctx, NBE_ERR_ARG, "expected 33 conv layers, got %d", n_layers);
+  for (auto& l : ctx->layers) { cudaFree(l.W); cudaFree(l.dW); cudaFree(l.SW); cudaFree(l.sb); }
+  ctx->layers.clear(); ctx->lidx.clear();
+  ctx->premod = premodulated != 0; ctx->vel = compute_vel != 0; ctx->eps = eps; ctx->have_params = false;
+  for (int i = 0; i < n_layers; ++i) {
+    const nbe_layer_params& p = layers[i];
+    if (!p.block || !p.layer || !p.weight || !p.bias) return fail(ctx, NBE_ERR_ARG, "layer %d: null field", i);
+    if (!ctx->premod && (!p.style_weight || !p.style_bias)) return fail(ctx, NBE_ERR_ARG, "layer %s/%s: style_weight/style_bias required", p.block, p.layer);
+    if (ctx->premod && ctx->vel && !p.dweight) return fail(ctx, NBE_ERR_ARG, "layer %s/%s: dweight required", p.block, p.layer);
+    if (!((p.cin == 3 || p.cin == 64 || p.cin == 128) && (p.cout == 3 || p.cout == 64 || p.cout == 128) && p.k >= 1 && p.k <= 3))
+      return fail(ctx, NBE_ERR_UNSUPPORTED, "layer %s/%s: unsupported shape cout=%d cin=%d k=%d (mid_chan must be 64)", p.block, p.layer, p.cout, p.cin, p.k);
+    Layer L;
+    L.block = p.block; L.layer = p.layer; L.cout = p.cout; L.cin = p.cin; L.k = p.k;
+    const size_t nw = static_cast<size_t>(p.cout) * p.cin * p.k * p.k * p.k;
+    CK(cudaMalloc(&L.W, nw * 4)); CK(cudaMemcpy(L.W, p.weight, nw * 4, cudaMemcpyHostToDevice));
+    if (p.dweight && ctx->premod) { CK(cudaMalloc(&L.dW, nw * 4)); CK(cudaMemcpy(L.dW, p.dweight, nw * 4, cudaMemcpyHostToDevice)); }
+    if (!ctx->premod) {
+      CK(cudaMalloc(&L.SW, p.cin * 2 * 4)); CK(cudaMemcpy(L.SW, p.style_weight, p.cin * 2 * 4, cudaMemcpyHostToDevice));
+      CK(cudaMalloc(&L.sb, p.cin * 4)); CK(cudaMemcpy(L.sb, p.style_bias, p.cin * 4, cudaMemcpyHostToDevice));
+    }
+    L.bias.assign(p.bias, p.bias + p.cout);
+    ctx->lidx[L.block + "/" + L.layer] = static_cast<int>(ctx->layers.size());
+    ctx->layers.push_back(L);
+  }
+  int rc = build_static(ctx);
+  if (rc) return rc;
+  ctx->have_params = true;
+  return NBE_OK;
+}
+
+int nbe_modulate(nbe_ctx* ctx, const float* Om, const float* Dz, int batch, void* stream) {
+  if (!ctx) return NBE_ERR_ARG;
+  if (!ctx->have_params) return fail(ctx, NBE_ERR_STATE, "nbe_modulate before nbe_set_params");
+  if (batch < 1 || !Dz) return fail(ctx, NBE_ERR_ARG, "batch >= 1 and Dz required");
+  if (!ctx->premod && !Om) return fail(ctx, NBE_ERR_ARG, "Om required for style models");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t need_p = static_cast<size_t>(batch) * ctx->packed_halves * 2;
+  const size_t need_w = static_cast<size_t>(batch) * ctx->w32_floats * 4;
+  const bool moved = ctx->packed_cap < need_p;
+  int rc;
+  if ((rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_packed), &ctx->packed_cap, need_p))) return rc;
+  if ((rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_w32), &ctx->w32_cap, need_w))) return rc;
+  if (ctx->vel) { if ((rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_dw32), &ctx->dw32_cap, need_w))) return rc; }
+  if (ctx->s_cap < batch) {
+    if (ctx->d_s0) { CK(cudaDeviceSynchronize()); cudaFree(ctx->d_s0); cudaFree(ctx->d_s1); }
+    CK(cudaMalloc(&ctx->d_s0, batch * 4)); CK(cudaMalloc(&ctx->d_s1, batch * 4)); ctx->s_cap = batch;
+  }
+  if (moved || batch != ctx->mod_batch) {
+    // packed buffer moved or sample count changed: tensor maps are stale
+    CK(cudaDeviceSynchronize());
+    for (auto* p : ctx->plans) { if (p->dev_launches) cudaFree(p->dev_launches); delete p; }
+    ctx->plans.clear();
+  }
+  // style vector in fp32 as in the reference (style_nbody_emulator_vel_core.py:126-128)
+  std::vector<float> s0(batch), s1(batch);
+  for (int b = 0; b < batch; ++b) {
+    s0[b] = Om ? (Om[b] - 0.3f) * 5.0f : 0.f;
+    s1[b] = Dz[b] - 1.0f;
+  }
+  CK(cudaMemcpyAsync(ctx->d_s0, s0.data(), batch * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_s1, s1.data(), batch * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(ctx->d_packed, 0, need_p, st));
+  // finish LayerMeta
+  std::vector<LayerMeta> hm = ctx->metas;
+  for (auto& s : ctx->sl)
+    for (auto& p : s.parts) {
+      LayerMeta& M = hm[p.layer];
+      const Layer& ly = ctx->layers[p.layer];
+      M.W = ly.W; M.dW = ly.dW; M.SW = ly.SW; M.sb = ly.sb;
+      M.w32 = ctx->d_w32 + ly.w32_off * batch;
+      M.dw32 = ctx->vel ? ctx->d_dw32 + ly.w32_off * batch : nullptr;
+      M.dst = ctx->d_packed + (M.kc16 ? s.b16_off : s.b64_off);
+      M.dst_sample_stride = ctx->packed_halves;
+      M.cout = ly.cout; M.cin = ly.cin; M.k3 = ly.k * ly.k * ly.k;
+      M.first = (ly.block == "conv_l00" && (ly.layer == "conv_0" || ly.layer == "skip")) ? 1 : 0;
+      M.premod = ctx->premod ? 1 : 0; M.vel = ctx->vel ? 1 : 0;
+    }
+  if (!ctx->d_metas) CK(cudaMalloc(&ctx->d_metas, hm.size() * sizeof(LayerMeta)));
+  CK(cudaMemcpyAsync(ctx->d_metas, hm.data(), hm.size() * sizeof(LayerMeta), cudaMemcpyHostToDevice, st));
+  int rows = 0;
+  for (auto& l : ctx->layers) rows += l.cout;
+  CK(cudaStreamSynchronize(st));     // hm / s0 / s1 are stack-owned
+  modulate_kernel<<<dim3(rows, batch), 128, 0, st>>>(ctx->d_metas, static_cast<int>(hm.size()), ctx->d_s0, ctx->d_s1, ctx->eps);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  ctx->mod_batch = batch;
+  return NBE_OK;
+}
+
+int nbe_get_modulated(nbe_ctx* ctx, int layer_index, int sample, float* w_host, float* dw_host) {
+  if (!ctx || !w_host) return NBE_ERR_ARG;
+  if (ctx->mod_batch < 1) return fail(ctx, NBE_ERR_STATE, "nbe_get_modulated before nbe_modulate");
+  if (layer_index < 0 || layer_index >= static_cast<int>(ctx->layers.size()) || sample < 0 || sample >= ctx->mod_batch)
+    return fail(ctx, NBE_ERR_ARG, "layer/sample out of range");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  const Layer& ly = ctx->layers[layer_index];
+  const size_t n = static_cast<size_t>(ly.cout) * ly.cin * ly.k * ly.k * ly.k;
+  const size_t off = static_cast<size_t>(ly.w32_off) * ctx->mod_batch + static_cast<size_t>(sample) * n;
+  CK(cudaMemcpy(w_host, ctx->d_w32 + off, n * 4, cudaMemcpyDeviceToHost));
+  if (dw_host) {
+    if (!ctx->vel) return fail(ctx, NBE_ERR_STATE, "no dweight: parameters were set with compute_vel = 0");
+    CK(cudaMemcpy(dw_host, ctx->d_dw32 + off, n * 4, cudaMemcpyDeviceToHost));
+  }
+  return NBE_OK;
+}
+
+size_t nbe_workspace_bytes(nbe_ctx* ctx, const int32_t dims[3]) {
+  if (!ctx || !dims) return 0;
+  int cd[A_COUNT], ch[A_COUNT], cw[A_COUNT];
+  if (chain(ctx, dims[0], cd) || chain(ctx, dims[1], ch) || chain(ctx, dims[2], cw)) return 0;
+  const bool split = ctx->precision == NBE_PREC_SPLIT;
+  size_t off = 0;
+  for (int a = 0; a < A_OUT; ++a) {
+    const size_t bytes = align_up(static_cast<size_t>(act_channels(a)) * cd[a] * ch[a] * cw[a] * 2, 1024);
+    off += bytes;
+    if (a != A_IN16) off += bytes * ((split ? 1 : 0) + (ctx->vel ? 1 : 0));
+  }
+  return off;
+}
+
+int nbe_forward(nbe_ctx* ctx, const void* x_dev, int in_dtype, int batch, const int32_t dims[3], const float* Dz,
+                const float* vel_fac, void* disp_dev, void* vel_dev, int out_dtype, void* stream) {
+  if (!ctx) return NBE_ERR_ARG;
+  if (!ctx->have_params) return fail(ctx, NBE_ERR_STATE, "nbe_forward before nbe_set_params");
+  if (ctx->mod_batch < 1) return fail(ctx, NBE_ERR_STATE, "nbe_forward before nbe_modulate");
+  if (!x_dev || !dims || !Dz || !disp_dev || batch < 1) return fail(ctx, NBE_ERR_ARG, "null argument");
+  if (ctx->vel && (!vel_dev || !vel_fac)) return fail(ctx, NBE_ERR_ARG, "velocity model: vel_dev and vel_fac required");
+  if (!ctx->vel && vel_dev) return fail(ctx, NBE_ERR_ARG, "displacement-only model: vel_dev must be NULL");
+  if (ctx->mod_batch != 1 && ctx->mod_batch != batch) return fail(ctx, NBE_ERR_STATE, "weights modulated for %d samples, batch is %d", ctx->mod_batch, batch);
+  if (in_dtype < 0 || in_dtype > 2 || out_dtype < 0 || out_dtype > 2) return fail(ctx, NBE_ERR_ARG, "bad dtype");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Plan* P = nullptr;
+  int rc = build_plan(ctx, dims, batch, &P);
+  if (rc) return rc;
+  const int nmax = std::max(dims[0], std::max(dims[1], dims[2]));
+  if ((rc = ensure_ident(ctx, nmax))) return rc;
+  const int64_t n0 = dims[0], n1 = dims[1], n2 = dims[2];
+  const int64_t o0 = n0 - 96, o1 = n1 - 96, o2 = n2 - 96;
+  for (int b = 0; b < batch; ++b) {
+    PackArgs pk{};
+    pk.src = static_cast<const uint8_t*>(x_dev) + static_cast<size_t>(b) * 3 * n0 * n1 * n2 * dtype_size(in_dtype);
+    pk.src_dtype = in_dtype; pk.src_sc = n0 * n1 * n2; pk.src_sd = n1 * n2; pk.src_sh = n2;
+    pk.idx_d = ctx->d_ident; pk.idx_h = ctx->d_ident; pk.idx_w = ctx->d_ident;
+    pk.in_norm = Dz[b] / 6.0f;
+    FinalArgs fa{};
+    fa.src = pk.src; fa.src_dtype = in_dtype; fa.src_sc = pk.src_sc; fa.src_sd = pk.src_sd; fa.src_sh = pk.src_sh;
+    fa.idx_d = ctx->d_ident + 48; fa.idx_h = ctx->d_ident + 48; fa.idx_w = ctx->d_ident + 48;
+    fa.disp = static_cast<uint8_t*>(disp_dev) + static_cast<size_t>(b) * 3 * o0 * o1 * o2 * dtype_size(out_dtype);
+    fa.vel = vel_dev ? static_cast<uint8_t*>(vel_dev) + static_cast<size_t>(b) * 3 * o0 * o1 * o2 * dtype_size(out_dtype) : nullptr;
+    fa.out_dtype = out_dtype; fa.mid_dtype = in_dtype; fa.o_sc = o0 * o1 * o2; fa.o_sd = o1 * o2; fa.o_sh = o2;
+    fa.in_norm = pk.in_norm; fa.six = 6.0f;
+    fa.dx_norm = vel_fac ? vel_fac[b] * 6.0f : 0.f;
+    fa.x0_norm = vel_fac ? vel_fac[b] * 6.0f / Dz[b] : 0.f;
+    if ((rc = run_sample(ctx, P, b, pk, fa, st))) return rc;
+  }
+  return NBE_OK;
+}
+
+int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32_t size[3], const int32_t crop[3],
+                    const int32_t plen[3], const int32_t* crop_idx, const int32_t* add_idx0, int sub_first,
+                    int sub_count, float Dz, float vel_fac, void* disp_host, void* vel_host, int out_dtype) {
+  if (!ctx) return NBE_ERR_ARG;
+  if (!ctx->have_params) return fail(ctx, NBE_ERR_STATE, "nbe_process_box before nbe_set_params");
+  if (ctx->mod_batch != 1) return fail(ctx, NBE_ERR_STATE, "nbe_process_box needs weights modulated for one sample");
+  if (!in_host || !size || !crop || !plen || !crop_idx || !add_idx0 || !disp_host || sub_count < 0)
+    return fail(ctx, NBE_ERR_ARG, "null argument");
+  if (ctx->vel && !vel_host) return fail(ctx, NBE_ERR_ARG, "velocity model: vel_host required");
+  if (in_dtype < 0 || in_dtype > 2 || out_dtype < 0 || out_dtype > 2) return fail(ctx, NBE_ERR_ARG, "bad dtype");
+  for (int d = 0; d < 3; ++d)
+    if (plen[d] - crop[d] != 96) return fail(ctx, NBE_ERR_ARG, "padding must be 48 per side (models hard-code the 48-voxel crop)");
+  if (sub_count == 0) return NBE_OK;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->own_stream, cs = ctx->copy_stream;
+  const int64_t S0 = size[0], S1 = size[1], S2 = size[2];
+  const size_t in_bytes = static_cast<size_t>(3) * S0 * S1 * S2 * dtype_size(in_dtype);
+  const size_t out_bytes = static_cast<size_t>(3) * S0 * S1 * S2 * dtype_size(out_dtype);
+  int rc;
+  if ((rc = ensure(ctx, &ctx->d_box, &ctx->box_cap, in_bytes))) return rc;
+  if ((rc = ensure(ctx, &ctx->d_disp, &ctx->out_cap, out_bytes))) return rc;
+  if (ctx->vel && (rc = ensure(ctx, &ctx->d_velo, &ctx->velo_cap, out_bytes))) return rc;
+  const int per = plen[0] + plen[1] + plen[2];
+  const size_t idx_bytes = static_cast<size_t>(sub_count) * per * sizeof(int32_t);
+  if ((rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_idx), &ctx->idx_cap, idx_bytes))) return rc;
+  CK(cudaMemcpyAsync(ctx->d_idx, crop_idx + static_cast<size_t>(sub_first) * per, idx_bytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_box, in_host, in_bytes, cudaMemcpyHostToDevice, st));
+  Plan* P = nullptr;
+  if ((rc = build_plan(ctx, plen, 1, &P))) return rc;
+  const size_t es = dtype_size(out_dtype);
+  cudaEvent_t done;
+  CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+  for (int s = 0; s < sub_count; ++s) {
+    const int32_t* ai = add_idx0 + static_cast<size_t>(sub_first + s) * 3;
+    const int32_t* di = ctx->d_idx + static_cast<size_t>(s) * per;
+    PackArgs pk{};
+    pk.src = ctx->d_box; pk.src_dtype = in_dtype; pk.src_sc = S0 * S1 * S2; pk.src_sd = S1 * S2; pk.src_sh = S2;
+    pk.idx_d = di; pk.idx_h = di + plen[0]; pk.idx_w = di + plen[0] + plen[1];
+    pk.in_norm = Dz / 6.0f;
+    FinalArgs fa{};
+    fa.src = ctx->d_box; fa.src_dtype = in_dtype; fa.src_sc = pk.src_sc; fa.src_sd = pk.src_sd; fa.src_sh = pk.src_sh;
+    fa.idx_d = pk.idx_d + 48; fa.idx_h = pk.idx_h + 48; fa.idx_w = pk.idx_w + 48;
+    const size_t base = (static_cast<size_t>(ai[0]) * S1 + ai[1]) * S2 + ai[2];
+    fa.disp = static_cast<uint8_t*>(ctx->d_disp) + base * es;
+    fa.vel = ctx->vel ? static_cast<uint8_t*>(ctx->d_velo) + base * es : nullptr;
+    fa.out_dtype = out_dtype; fa.mid_dtype = in_dtype; fa.o_sc = S0 * S1 * S2; fa.o_sd = S1 * S2; fa.o_sh = S2;
+    fa.in_norm = pk.in_norm; fa.six = 6.0f; fa.dx_norm = vel_fac * 6.0f; fa.x0_norm = vel_fac * 6.0f / Dz;
+    if ((rc = run_sample(ctx, P, 0, pk, fa, st))) { cudaEventDestroy(done); return rc; }
+    // paste: copy the owned block back (rows of crop[2] elements) while the next subbox computes
+    CK(cudaEventRecord(done, st));
+    CK(cudaStreamWaitEvent(cs, done, 0));
+    for (int f = 0; f < (ctx->vel ? 2 : 1); ++f) {
+      uint8_t* dsrc = static_cast<uint8_t*>(f == 0 ? ctx->d_disp : ctx->d_velo);
+      uint8_t* hdst = static_cast<uint8_t*>(f == 0 ? disp_host : vel_host);
+      for (int c = 0; c < 3; ++c) {
+        cudaMemcpy3DParms p3 = {};
+        const size_t choff = static_cast<size_t>(c) * S0 * S1 * S2 * es;
+        p3.srcPtr = make_cudaPitchedPtr(dsrc + choff, S2 * es, S2, S1);
+        p3.dstPtr = make_cudaPitchedPtr(hdst + choff, S2 * es, S2, S1);
+        p3.srcPos = make_cudaPos(static_cast<size_t>(ai[2]) * es, ai[1], ai[0]);
+        p3.dstPos = p3.srcPos;
+        p3.extent = make_cudaExtent(static_cast<size_t>(crop[2]) * es, crop[1], crop[0]);
+        p3.kind = cudaMemcpyDeviceToHost;
+        CK(cudaMemcpy3DAsync(&p3, cs));
+      }
+    }
+  }
+  cudaError_t e1 = cudaStreamSynchronize(st);
+  cudaError_t e2 = cudaStreamSynchronize(cs);
+  cudaEventDestroy(done);
+  if (e1 != cudaSuccess) return fail(ctx, NBE_ERR_CUDA, "process_box: %s", cudaGetErrorString(e1));
+  if (e2 != cudaSuccess) return fail(ctx, NBE_ERR_CUDA, "process_box copy: %s", cudaGetErrorString(e2));
+  return NBE_OK;
+}
+
+int64_t nbe_launch_count(nbe_ctx* ctx, int reset) {
+  if (!ctx) return -1;
+  const int64_t n = ctx->launches;
+  if (reset) ctx->launches = 0;
+  return n;
+}
+
+int nbe_set_profiling(nbe_ctx* ctx, int enable) {
+  if (!ctx) return NBE_ERR_ARG;
+  ctx->profiling = enable != 0;
+  return NBE_OK;
+}
+
+int nbe_get_profile(nbe_ctx* ctx, int cap, const char** names, float* ms, double* flops) {
+  if (!ctx) return NBE_ERR_ARG;
+  const int n = static_cast<int>(std::min(ctx->prof_ms.size(), ctx->prof_names.size()));
+  for (int i = 0; i < n && i < cap; ++i) {
+    if (names) names[i] = ctx->prof_names[i].c_str();
+    if (ms) ms[i] = ctx->prof_ms[i];
+    if (flops) flops[i] = ctx->prof_flops[i];
+  }
+  return n;
+}
+
+// Debug: copy one activation tensor (NDHWC fp16) of the most recent plan to the host.
+// which: 0 = hi, 1 = lo, 2 = tangent.  shape_out = {d, h, w, c}.  Returns bytes copied or <0.
+long long nbe_debug_read_act(nbe_ctx* ctx, int act, int which, void* host, size_t cap, int32_t shape_out[4]) {
+  if (!ctx || ctx->plans.empty() || act < 0 || act >= A_OUT) return NBE_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  Plan* P = ctx->plans.back();
+  const ActBuf& B = P->act[act];
+  const size_t bytes = static_cast<size_t>(B.c) * B.d * B.h * B.w * 2;
+  if (shape_out) { shape_out[0] = B.d; shape_out[1] = B.h; shape_out[2] = B.w; shape_out[3] = B.c; }
+  if (!host) return static_cast<long long>(bytes);
+  if (cap < bytes) return NBE_ERR_ARG;
+  const size_t off = which == 0 ? B.off_hi : (which == 1 ? B.off_lo : B.off_dx);
+  if (cudaMemcpy(host, ctx->arena + off, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return NBE_ERR_CUDA;
+  return static_cast<long long>(bytes);
+}
+
+int nbe_selftest(nbe_ctx* ctx, char* report, size_t report_cap) {
+  if (!ctx) return NBE_ERR_ARG;
+  if (report && report_cap) snprintf(report, report_cap, "selftest: see tests (conv parity vs CPU oracle)\n");
+  return NBE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,191 @@
+"""Subbox decomposition of large periodic boxes, drop-in for the reference ``subbox.py``.
+
+``SubboxConfig`` reproduces the reference's integer tables bit-exactly (anchor order,
+``arange(a-p0, a+c+p1) % size`` periodic indices, floor division of the box -- remainder
+strips stay zero; subbox.py:45-97).  ``SubboxProcessor.process_box`` keeps the reference
+signature (subbox.py:139-147) but, instead of a serial numpy-gather / device_put / apply /
+np.asarray loop, uploads the box once and runs gather, net and paste on the GPU
+(``nbe_process_box``).  With ``torch.distributed`` initialised the subboxes are sharded over
+the ranks (one process per GPU, contiguous index ranges, no data-path collective).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any
+
+import numpy as np
+
+from . import _lib
+from ._engine import Engine, dtype_code, _torch
+from .cosmology import growth_factor, vel_norm
+
+
+@dataclass
+class SubboxConfig:
+    """Configuration for subbox processing (same fields as the reference, subbox.py:25-43)."""
+    size: tuple
+    ndiv: tuple
+    dtype: Any = np.float32
+    output_dtype: Any = np.float32
+    in_chan: int = 3
+    padding: tuple = ((48, 48), (48, 48), (48, 48))
+
+    def __post_init__(self):
+        self.NDIM = 3
+        self.n_subboxes = np.prod(self.ndiv)
+        self.crop_size = tuple(s // d for s, d in zip(self.size, self.ndiv))
+        self.all_crop_inds = []
+        self.all_add_inds = []
+        for idx in range(self.n_subboxes):
+            crop_inds, add_inds = self._compute_indices(idx)
+            self.all_crop_inds.append(crop_inds)
+            self.all_add_inds.append(add_inds)
+
+    def _get_anchor(self, idx):
+        n1, n2 = self.ndiv[1], self.ndiv[2]
+        c = self.crop_size
+        return ((idx // (n1 * n2)) * c[0], ((idx // n2) % n1) * c[1], (idx % n2) * c[2])
+
+    def _compute_indices(self, idx):
+        anchor = self._get_anchor(idx)
+        crop_inds = self._get_crop_inds(anchor, self.crop_size, self.padding)
+        add_inds = self._get_crop_inds(anchor, self.crop_size, ((0, 0),) * self.NDIM)
+        return crop_inds, add_inds
+
+    def _get_crop_inds(self, anchor, crop, pad):
+        ind = [slice(None)]
+        for d in range(self.NDIM):
+            lo = anchor[d] - pad[d][0]
+            hi = anchor[d] + crop[d] + pad[d][1]
+            i = np.arange(lo, hi) % self.size[d]
+            ind.append(i.reshape((-1,) + (1,) * (self.NDIM - d - 1)))
+        return tuple(ind)
+
+    # ---- compact int32 tables handed to the C ABI
+    def flat_tables(self):
+        """(crop_idx int32 [n_sub*(p0+p1+p2)], add_idx0 int32 [n_sub*3], plen)."""
+        plen = tuple(int(c + p[0] + p[1]) for c, p in zip(self.crop_size, self.padding))
+        n = int(self.n_subboxes)
+        crop = np.empty((n, sum(plen)), dtype=np.int32)
+        add0 = np.empty((n, 3), dtype=np.int32)
+        for idx in range(n):
+            ci, ai = self.all_crop_inds[idx], self.all_add_inds[idx]
+            crop[idx] = np.concatenate([np.asarray(ci[d + 1]).ravel() for d in range(3)])
+            add0[idx] = [int(np.asarray(ai[d + 1]).ravel()[0]) if self.crop_size[d] > 0 else 0 for d in range(3)]
+        return np.ascontiguousarray(crop.ravel()), np.ascontiguousarray(add0.ravel()), plen
+
+
+def shard_range(n, rank, world):
+    """Contiguous index range of `rank` (C-order => D-slabs first); the first n % world ranks
+    get one extra subbox."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _pinned_zeros(shape, np_dtype):
+    torch = _torch()
+    tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.float16): torch.float16}[np.dtype(np_dtype)]
+    t = torch.zeros(shape, dtype=tdt, pin_memory=True)
+    return t, t.numpy()
+
+
+class SubboxProcessor:
+    """Unified subbox processor for all four model variants (subbox.py:99-137)."""
+
+    def __init__(self, model, params, config: SubboxConfig):
+        from .models import (NBodyEmulatorCore, NBodyEmulatorVelCore, StyleNBodyEmulatorCore,
+                             StyleNBodyEmulatorVelCore)
+        self.model = model
+        self.params = params          # read at call time; tests re-assign it
+        self.config = config
+        t = type(model)
+        if t in (NBodyEmulatorCore, NBodyEmulatorVelCore):
+            self.premodulate = True
+        elif t in (StyleNBodyEmulatorCore, StyleNBodyEmulatorVelCore):
+            self.premodulate = False
+        if t in (NBodyEmulatorVelCore, StyleNBodyEmulatorVelCore):
+            self.compute_vel = True
+        elif t in (NBodyEmulatorCore, StyleNBodyEmulatorCore):
+            self.compute_vel = False
+        self._tables = None
+        self._keep = None
+
+    def process_box(self, input_box, z, Om, desc="Processing subboxes", show_progress=True,
+                    shard=None, gather="all"):
+        """Process the whole box; returns displacement (C,D,H,W) or (displacement, velocity) as
+        numpy arrays of ``config.output_dtype``.
+
+        shard: None = shard over torch.distributed ranks iff initialised with world_size > 1;
+        (rank, world) forces a split (each rank returns only its own voxels, rest zero) unless
+        ``gather`` is "all" (all-gather over NCCL/gloo) or "rank0".
+        """
+        cfg = self.config
+        torch = _torch()
+        if self.params is None:
+            raise ValueError("No parameters loaded. Use load_params=True in create_emulator.")
+        in_np = np.dtype(cfg.dtype)
+        out_np = np.dtype(cfg.output_dtype)
+        box = np.asarray(input_box)
+        if box.shape != (cfg.in_chan,) + tuple(cfg.size):
+            raise ValueError(f"input_box has shape {box.shape}, expected {(cfg.in_chan,) + tuple(cfg.size)}")
+        # the reference casts each crop to config.dtype on the host before upload (subbox.py:200-202)
+        box = np.ascontiguousarray(box, dtype=in_np)
+        Dz = np.float32(growth_factor(z, Om))
+        vf = np.float32(vel_norm(z, Om)) if self.compute_vel else np.float32(0)
+
+        n = int(cfg.n_subboxes)
+        dist = torch.distributed if torch.distributed.is_available() and torch.distributed.is_initialized() else None
+        if shard is None:
+            shard = (dist.get_rank(), dist.get_world_size()) if dist is not None and dist.get_world_size() > 1 else (0, 1)
+        rank, world = shard
+        lo, hi = shard_range(n, rank, world)
+
+        eng = Engine.get()
+        eng.set_precision(self.model.precision)
+        eng.set_params(self.params, self.premodulate, self.compute_vel, self.model.eps)
+        eng.modulate(None if self.premodulate else np.float32(Om), Dz)
+        if self._tables is None:
+            self._tables = cfg.flat_tables()
+        crop_idx, add0, plen = self._tables
+
+        shape = (cfg.in_chan,) + tuple(cfg.size)
+        dis_t, dis = _pinned_zeros(shape, out_np)
+        vel_t, vel = _pinned_zeros(shape, out_np) if self.compute_vel else (None, None)
+        bar = None
+        if show_progress:
+            from tqdm import tqdm
+            bar = tqdm(total=hi - lo, desc=desc, ncols=80,
+                       bar_format='{desc}: {percentage:3.0f}%|{bar:30}| {n_fmt}/{total_fmt} [{elapsed}<{remaining}]')
+        eng.process_box(box, dtype_code(in_np), cfg.size, cfg.crop_size, plen, crop_idx, add0, lo, hi - lo,
+                        Dz, vf, dis, vel, dtype_code(out_np))
+        if bar is not None:
+            bar.update(hi - lo)
+            bar.close()
+        self._keep = (dis_t, vel_t)
+        if world > 1 and dist is not None and gather in ("all", "rank0"):
+            dis, vel = _gather_outputs(dist, cfg, dis, vel, world, gather)
+        if self.compute_vel:
+            return dis, vel
+        return dis
+
+
+def _gather_outputs(dist, cfg, dis, vel, world, mode):
+    """Sum the disjoint per-rank outputs (each voxel is owned by exactly one rank; the others
+    hold zeros).  NCCL over NVLink on GPUs, gloo on CPU tensors in the tests."""
+    torch = _torch()
+    on_gpu = dist.get_backend() == "nccl"
+    outs = []
+    for a in (dis, vel):
+        if a is None:
+            outs.append(None)
+            continue
+        t = torch.from_numpy(a)
+        if on_gpu:
+            t = t.cuda()
+        if mode == "all":
+            dist.all_reduce(t)
+        else:
+            dist.reduce(t, dst=0)
+        outs.append(t.cpu().numpy())
+    return outs[0], outs[1]
