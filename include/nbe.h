@@ -108,13 +108,22 @@ int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32
                     const int32_t* add_idx0, int sub_first, int sub_count, float Dz, float vel_fac,
                     void* disp_host, void* vel_host, int out_dtype);
 
+/* Same decomposition with the box and the outputs resident in device memory ((3,size) each);
+ * asynchronous on `stream`, no host<->device traffic besides the index tables.            */
+int nbe_process_box_dev(nbe_ctx* ctx, const void* box_dev, int in_dtype, const int32_t size[3],
+                        const int32_t crop[3], const int32_t plen[3], const int32_t* crop_idx,
+                        const int32_t* add_idx0, int sub_first, int sub_count, float Dz, float vel_fac,
+                        void* disp_dev, void* vel_dev, int out_dtype, void* stream);
+
 /* Bytes of device memory the context needs for one (n0,n1,n2) sample (activation arena). */
 size_t nbe_workspace_bytes(nbe_ctx* ctx, const int32_t dims[3]);
 
 /* Instrumentation: kernels launched by this context since the last reset, and per-launch
- * device timings (CUDA events on the launching stream) of the most recent nbe_forward of
- * sample 0 when profiling is enabled.  names/ms/flops arrays hold up to `cap` entries;
- * returns the number of launches recorded.                                               */
+ * device timings: while profiling is enabled every launch is bracketed by CUDA events on the
+ * launching stream (no synchronisation); nbe_get_profile resolves them and returns, per
+ * launch slot, the name, the mean duration in ms over all samples run since profiling was
+ * enabled and the algorithmic FLOPs of one launch.  Arrays hold up to `cap` entries; returns
+ * the number of slots.                                                                    */
 int64_t nbe_launch_count(nbe_ctx* ctx, int reset);
 int nbe_set_profiling(nbe_ctx* ctx, int enable);
 int nbe_get_profile(nbe_ctx* ctx, int cap, const char** names, float* ms, double* flops);

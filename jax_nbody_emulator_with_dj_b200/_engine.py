@@ -234,6 +234,19 @@ class Engine:
             float(vel_fac), C.c_void_p(disp_host.ctypes.data),
             C.c_void_p(vel_host.ctypes.data) if vel_host is not None else None, out_code))
 
+    def process_box_dev(self, box_dev, size, crop, plen, crop_idx, add_idx0, first, count, Dz, vel_fac,
+                        disp_dev, vel_dev):
+        """Device-resident variant: torch CUDA tensors (3,size) in / out, async on the current stream."""
+        torch = _torch()
+        ip = C.POINTER(C.c_int32)
+        a3 = lambda t: (C.c_int32 * 3)(*[int(v) for v in t])
+        self._ck(self.lib.nbe_process_box_dev(
+            self.h, C.c_void_p(box_dev.data_ptr()), dtype_code(box_dev.dtype), a3(size), a3(crop), a3(plen),
+            crop_idx.ctypes.data_as(ip), add_idx0.ctypes.data_as(ip), int(first), int(count), float(Dz),
+            float(vel_fac), C.c_void_p(disp_dev.data_ptr()),
+            C.c_void_p(vel_dev.data_ptr()) if vel_dev is not None else None, dtype_code(disp_dev.dtype),
+            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
     # ---- instrumentation
     def launch_count(self, reset=False):
         return int(self.lib.nbe_launch_count(self.h, int(reset)))

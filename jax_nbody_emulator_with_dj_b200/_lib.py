@@ -21,7 +21,8 @@ NBE_PREC_SPLIT, NBE_PREC_FP16 = 0, 1
 
 EXPORTS = (
     "nbe_create", "nbe_destroy", "nbe_last_error", "nbe_version", "nbe_set_params", "nbe_set_precision",
-    "nbe_modulate", "nbe_get_modulated", "nbe_forward", "nbe_process_box", "nbe_workspace_bytes",
+    "nbe_modulate", "nbe_get_modulated", "nbe_forward", "nbe_process_box", "nbe_process_box_dev",
+    "nbe_workspace_bytes",
     "nbe_launch_count", "nbe_set_profiling", "nbe_get_profile", "nbe_selftest", "nbe_debug_read_act",
 )
 
@@ -83,6 +84,8 @@ def load():
         lib.nbe_forward.argtypes = [vp, vp, C.c_int, C.c_int, i32p, f32p, f32p, vp, vp, C.c_int, vp]
         lib.nbe_process_box.argtypes = [vp, vp, C.c_int, i32p, i32p, i32p, i32p, i32p, C.c_int, C.c_int,
                                         C.c_float, C.c_float, vp, vp, C.c_int]
+        lib.nbe_process_box_dev.argtypes = [vp, vp, C.c_int, i32p, i32p, i32p, i32p, i32p, C.c_int, C.c_int,
+                                            C.c_float, C.c_float, vp, vp, C.c_int, vp]
         lib.nbe_workspace_bytes.argtypes = [vp, i32p]
         lib.nbe_workspace_bytes.restype = C.c_size_t
         lib.nbe_launch_count.argtypes = [vp, C.c_int]

@@ -50,12 +50,18 @@ struct GroupDesc {
   MmaOp ops[3];
 };
 
+// Passed by value as a __grid_constant__ kernel parameter: lives in the constant bank, so the
+// pipeline warps read it with uniform loads straight into uniform registers.
+struct GroupTable {
+  int32_t n_groups;
+  int32_t pad_[3];
+  GroupDesc g[kMaxGroups];
+};
+
 struct alignas(128) ConvLaunch {
   CUtensorMap amap[kMaxAMaps];
   CUtensorMap bmap64;
   CUtensorMap bmap16;
-  GroupDesc groups[kMaxGroups];
-  int32_t n_groups;
   int32_t n_par;            // 1, or 8 for the x2 up-sampling conv (one parity per item)
   int32_t par_brow_step;    // B rows between parities
   int32_t out_w, out_h, out_d;         // extent of the tile space
@@ -118,21 +124,23 @@ struct ConvCfg {
   static constexpr int kAStage = 2 * kABlk;
   static constexpr int kBStage = NRS * 128;
   static constexpr int kNA = (TM == 1) ? 3 : 2;
-  static constexpr int kBudget = kSmemLimit - 1024 /*align*/ - 1024 /*barriers+bias*/ - kNA * kAStage;
+  static constexpr int kCtrl = 2048;                       // barriers, TMEM slot, bias
+  static constexpr int kBudget = kSmemLimit - 1024 /*align*/ - kCtrl - kNA * kAStage;
   static constexpr int kNBraw = kBudget / kBStage;
   static constexpr int kNB = kNBraw > 6 ? 6 : kNBraw;
   static constexpr int kNBuf = (2 * TM * DC <= 512) ? 2 : 1;
   static constexpr int kColsRaw = kNBuf * TM * DC;
   static constexpr int kTmemCols = kColsRaw <= 32 ? 32 : kColsRaw <= 64 ? 64 : kColsRaw <= 128 ? 128
                                    : kColsRaw <= 256 ? 256 : 512;
-  static constexpr int kSmemBytes = 1024 + kNA * kAStage + kNB * kBStage + 1024;
+  static constexpr int kSmemBytes = 1024 + kNA * kAStage + kNB * kBStage + kCtrl;
   static_assert(kNB >= 2, "not enough shared memory for the B ring");
   static_assert(kColsRaw <= 512, "TMEM overflow");
 };
 
 template <int NRS, int DC, int TM, bool FINAL>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_mma_kernel(const ConvLaunch* __restrict__ L, const FinalArgs fa) {
+conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupTable gt,
+                const __grid_constant__ FinalArgs fa) {
   using Cfg = ConvCfg<NRS, DC, TM>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -153,7 +161,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const FinalArgs fa) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int n_groups = L->n_groups;
+  const int n_groups = gt.n_groups;
   const int out_w = L->out_w, out_h = L->out_h, out_d = L->out_d;
   const int tiles_w = (out_w + 7) >> 3;
   const int tiles_h = (out_h + 16 * TM - 1) / (16 * TM);
@@ -193,7 +201,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const FinalArgs fa) {
         int par, w0, h0, d0;
         decode(item, par, w0, h0, d0);
         for (int g = 0; g < n_groups; ++g) {
-          const GroupDesc& G = L->groups[g];
+          const GroupDesc& G = gt.g[g];
           const uint32_t blk = G.kc16 ? Cfg::kRows * 32 : Cfg::kABlk;
           mbar_wait(&a_empty[s], ph ^ 1);
           mbar_expect_tx(&a_full[s], blk * G.n_a);
@@ -212,7 +220,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const FinalArgs fa) {
         int par, w0, h0, d0;
         decode(item, par, w0, h0, d0);
         for (int g = 0; g < n_groups; ++g) {
-          const GroupDesc& G = L->groups[g];
+          const GroupDesc& G = gt.g[g];
           const CUtensorMap* bm = G.kc16 ? &L->bmap16 : &L->bmap64;
           const uint32_t bytes = G.kc16 ? NRS * 32 : NRS * 128;
           const int row0 = G.brow0 + par * L->par_brow_step;
@@ -226,49 +234,74 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const FinalArgs fa) {
       }
     }
   } else if (warp == 2) {
-    // ------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc_base = umma_idesc_f16(128, 0, false);
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, buf = 0, pacc = 0;
-      for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-        mbar_wait(&acc_empty[buf], pacc ^ 1);
+    // ------------------------------------------------ MMA issuer
+    // The whole warp runs this loop with warp-uniform control flow and values (so they stay in
+    // uniform registers); lane 0 alone issues tcgen05.mma / tcgen05.commit.
+    constexpr uint32_t idesc_base = umma_idesc_f16(128, 0, false);
+    const uint32_t issuer = lane == 0 ? 1u : 0u;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, buf = 0, pacc = 0;
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+      mbar_wait(&acc_empty[buf], pacc ^ 1);
+      tc_fence_after();
+      for (int g = 0; g < n_groups; ++g) {
+        const GroupDesc& G = gt.g[g];
+        const int ntaps = G.ntaps, n_ops = G.n_ops;
+        const bool k16 = G.kc16 != 0;
+        const uint32_t rowb = k16 ? 32u : 128u;
+        const uint32_t sbo16 = rowb >> 1;                       // (8 rows * rowb) >> 4
+        // upper descriptor word: SBO | version | layout
+        const uint32_t desc_hi = sbo16 | (1u << 14) | ((k16 ? 6u : 2u) << 29);
+        uint32_t op_a[3], op_b[3], op_d[3], op_i[3];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          op_a[o] = (static_cast<uint32_t>(G.ops[o].a) * Cfg::kABlk) >> 4;
+          op_b[o] = (static_cast<uint32_t>(G.ops[o].b_row) * rowb) >> 4;
+          op_d[o] = G.ops[o].d_col;
+          op_i[o] = idesc_base | (static_cast<uint32_t>(G.ops[o].n8) << 17);
+        }
+        mbar_wait(&a_full[sa], pa);
         tc_fence_after();
-        for (int g = 0; g < n_groups; ++g) {
-          const GroupDesc& G = L->groups[g];
-          const uint32_t rowb = G.kc16 ? 32u : 128u;
-          const uint32_t sbo = rowb * 8u;
-          const uint64_t lay = G.kc16 ? UMMA_SW32 : UMMA_SW128;
-          const int ksteps = G.kc16 ? 1 : 4;
-          mbar_wait(&a_full[sa], pa);
+        const uint32_t a_lo = ((smem_u32(a_smem + sa * Cfg::kAStage) & 0x3FFFFu) >> 4) | (1u << 16);
+        for (int j = 0; j < ntaps; ++j) {
+          mbar_wait(&b_full[sb], pb);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(a_smem + sa * Cfg::kAStage);
-          for (int j = 0; j < G.ntaps; ++j) {
-            mbar_wait(&b_full[sb], pb);
-            tc_fence_after();
-            const uint32_t b_base = smem_u32(b_smem + sb * Cfg::kBStage);
+          const uint32_t b_lo = ((smem_u32(b_smem + sb * Cfg::kBStage) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t first = (g | j) == 0 ? 0u : 1u;
+          {
 #pragma unroll
             for (int t = 0; t < TM; ++t) {
-              const uint32_t d_tile = tmem_base + (buf * TM + t) * DC;
-              const uint32_t a_row = static_cast<uint32_t>(t * 16 + j) * sbo;
-              for (int k = 0; k < ksteps; ++k) {
-                for (int o = 0; o < G.n_ops; ++o) {
-                  const MmaOp op = G.ops[o];
-                  const uint64_t ad = umma_smem_desc(a_base + op.a * Cfg::kABlk + a_row + k * 32, sbo, lay);
-                  const uint64_t bd = umma_smem_desc(b_base + op.b_row * rowb + k * 32, sbo, lay);
-                  const uint32_t acc = (g | j | k | o) != 0 ? 1u : 0u;
-                  umma_f16(d_tile + op.d_col, ad, bd, idesc_base | (static_cast<uint32_t>(op.n8) << 17), acc);
+              const uint32_t d_tile = tmem_u + (buf * TM + t) * DC;
+              const uint32_t a_row = static_cast<uint32_t>(t * 16 + j) * sbo16;
+              if (k16) {
+#pragma unroll
+                for (int o = 0; o < 3; ++o)
+                  if (o < n_ops)
+                    umma_f16_pred(d_tile + op_d[o], (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + op_a[o] + a_row),
+                                  (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + op_b[o]), op_i[o],
+                                  o == 0 ? first : 1u, issuer);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                  for (int o = 0; o < 3; ++o)
+                    if (o < n_ops)
+                      umma_f16_pred(d_tile + op_d[o],
+                                    (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + op_a[o] + a_row + 2u * k),
+                                    (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + op_b[o] + 2u * k), op_i[o],
+                                    (k | o) == 0 ? first : 1u, issuer);
                 }
               }
             }
-            umma_commit(&b_empty[sb]);
-            if (++sb == Cfg::kNB) { sb = 0; pb ^= 1; }
+            umma_commit_pred(&b_empty[sb], issuer);
           }
-          umma_commit(&a_empty[sa]);
-          if (++sa == Cfg::kNA) { sa = 0; pa ^= 1; }
+          if (++sb == Cfg::kNB) { sb = 0; pb ^= 1; }
         }
-        umma_commit(&acc_full[buf]);
-        if (++buf == Cfg::kNBuf) { buf = 0; pacc ^= 1; }
+        umma_commit_pred(&a_empty[sa], issuer);
+        if (++sa == Cfg::kNA) { sa = 0; pa ^= 1; }
       }
+      umma_commit_pred(&acc_full[buf], issuer);
+      if (++buf == Cfg::kNBuf) { buf = 0; pacc ^= 1; }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue (128 threads, thread <-> row)

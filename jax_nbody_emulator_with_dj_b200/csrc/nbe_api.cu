@@ -57,6 +57,7 @@ struct ActBuf { int c = 0, d = 0, h = 0, w = 0; size_t off_hi = 0, off_lo = 0, o
 
 struct HostLaunch {
   ConvLaunch L;
+  GroupTable G;
   int inst;
   int grid;
   double flops;
@@ -124,9 +125,11 @@ struct nbe_ctx {
   // instrumentation
   int64_t launches = 0;
   bool profiling = false;
-  std::vector<std::string> prof_names;
-  std::vector<float> prof_ms;
+  std::vector<std::string> prof_names;      // per launch slot (pack_input + conv launches)
   std::vector<double> prof_flops;
+  std::vector<cudaEvent_t> prof_events;     // (slots+1) events per recorded sample, resolved lazily
+  std::vector<double> prof_sum_ms;
+  long long prof_samples = 0;
 };
 
 namespace {
@@ -421,6 +424,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
       H.inst = s.inst; H.name = s.name; H.flops = 0;
       ConvLaunch& Lc = H.L;
       memset(&Lc, 0, sizeof Lc);
+      memset(&H.G, 0, sizeof H.G);
       const int box_h = 16 * ii.tm + 2;
       std::map<std::pair<const void*, int>, int> amap;
       int n_amap = 0;
@@ -439,7 +443,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
 
       int ng = 0;
       bool bad = false;
-      auto push = [&](const GroupDesc& G) { if (ng < kMaxGroups) Lc.groups[ng++] = G; else bad = true; };
+      auto push = [&](const GroupDesc& G) { if (ng < kMaxGroups) H.G.g[ng++] = G; else bad = true; };
       const int nkind = (vel && split) ? 2 : 1;
       const ActBuf& OB = P->act[s.out_act];
       // tile space = output voxels, except for the up-sampling conv (input voxels)
@@ -542,7 +546,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
         }
       }
       if (bad) { delete P; return fail(ctx, NBE_ERR_STATE, "launch %s: too many groups / tensor maps", s.name.c_str()); }
-      Lc.n_groups = ng;
+      H.G.n_groups = ng;
       Lc.cout = s.cout; Lc.vel = vel ? 1 : 0; Lc.act = 1;
       Lc.bias = ctx->d_bias + s.bias_off;
       if (!ii.fin) {
@@ -578,7 +582,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
 }
 
 template <int NRS, int DC, int TM, bool FIN>
-cudaError_t launch_inst(const ConvLaunch* dl, const FinalArgs& fa, int grid, cudaStream_t st) {
+cudaError_t launch_inst(const ConvLaunch* dl, const GroupTable& gt, const FinalArgs& fa, int grid, cudaStream_t st) {
   using Cfg = ConvCfg<NRS, DC, TM>;
   static bool attr_set = false;
   auto kern = conv_mma_kernel<NRS, DC, TM, FIN>;
@@ -587,18 +591,18 @@ cudaError_t launch_inst(const ConvLaunch* dl, const FinalArgs& fa, int grid, cud
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(dl, fa);
+  kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(dl, gt, fa);
   return cudaGetLastError();
 }
 
-cudaError_t launch_conv(int inst, const ConvLaunch* dl, const FinalArgs& fa, int grid, cudaStream_t st) {
+cudaError_t launch_conv(int inst, const ConvLaunch* dl, const GroupTable& gt, const FinalArgs& fa, int grid, cudaStream_t st) {
   switch (inst) {
-    case I_128_128_2: return launch_inst<128, 128, 2, false>(dl, fa, grid, st);
-    case I_256_256_1: return launch_inst<256, 256, 1, false>(dl, fa, grid, st);
-    case I_FINAL: return launch_inst<32, 16, 2, true>(dl, fa, grid, st);
-    case I_128_64_2: return launch_inst<128, 64, 2, false>(dl, fa, grid, st);
-    case I_64_64_2: return launch_inst<64, 64, 2, false>(dl, fa, grid, st);
-    case I_256_128_2: return launch_inst<256, 128, 2, false>(dl, fa, grid, st);
+    case I_128_128_2: return launch_inst<128, 128, 2, false>(dl, gt, fa, grid, st);
+    case I_256_256_1: return launch_inst<256, 256, 1, false>(dl, gt, fa, grid, st);
+    case I_FINAL: return launch_inst<32, 16, 2, true>(dl, gt, fa, grid, st);
+    case I_128_64_2: return launch_inst<128, 64, 2, false>(dl, gt, fa, grid, st);
+    case I_64_64_2: return launch_inst<64, 64, 2, false>(dl, gt, fa, grid, st);
+    case I_256_128_2: return launch_inst<256, 128, 2, false>(dl, gt, fa, grid, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -610,33 +614,51 @@ int run_sample(nbe_ctx* ctx, Plan* P, int sample, PackArgs pk, FinalArgs fa, cud
   pk.n0 = P->dims[0]; pk.n1 = P->dims[1]; pk.n2 = P->dims[2];
   const long long nvox = 1ll * pk.n0 * pk.n1 * pk.n2;
   const int pgrid = static_cast<int>(std::min<long long>((nvox + 255) / 256, 148ll * 16));
-  const bool prof = ctx->profiling && sample == 0;
-  std::vector<cudaEvent_t> ev;
-  auto mark = [&]() { if (prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); } };
-  if (prof) { ctx->prof_names.clear(); ctx->prof_ms.clear(); ctx->prof_flops.clear(); }
+  const int slots = P->n_launch + 1;
+  const bool prof = ctx->profiling && ctx->prof_events.size() < 400000;
+  if (prof && static_cast<int>(ctx->prof_names.size()) != slots) {
+    ctx->prof_names.assign(1, "pack_input");
+    ctx->prof_flops.assign(1, 0.0);
+    for (int li = 0; li < P->n_launch; ++li) {
+      ctx->prof_names.push_back(P->launches[li].name);
+      ctx->prof_flops.push_back(P->launches[li].flops);
+    }
+    ctx->prof_sum_ms.assign(slots, 0.0);
+    ctx->prof_samples = 0;
+  }
+  auto mark = [&]() {
+    if (prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ctx->prof_events.push_back(e); }
+  };
   mark();
   pack_input_kernel<<<pgrid, 256, 0, st>>>(pk);
   CK(cudaGetLastError());
   ctx->launches++;
-  if (prof) { ctx->prof_names.push_back("pack_input"); ctx->prof_flops.push_back(0.0); }
   mark();
   for (int li = 0; li < P->n_launch; ++li) {
     const HostLaunch& H = P->launches[static_cast<size_t>(sample) * P->n_launch + li];
-    CK(launch_conv(H.inst, P->dev_launches + static_cast<size_t>(sample) * P->n_launch + li, fa, H.grid, st));
+    CK(launch_conv(H.inst, P->dev_launches + static_cast<size_t>(sample) * P->n_launch + li, H.G, fa, H.grid, st));
     ctx->launches++;
-    if (prof) { ctx->prof_names.push_back(H.name); ctx->prof_flops.push_back(H.flops); }
     mark();
   }
-  if (prof) {
-    CK(cudaStreamSynchronize(st));
-    for (size_t i = 0; i + 1 < ev.size(); ++i) {
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
-      ctx->prof_ms.push_back(ms);
-    }
-    for (auto e : ev) cudaEventDestroy(e);
-  }
   return NBE_OK;
+}
+
+// fold the recorded events into per-slot sums (synchronises the device)
+void resolve_profile(nbe_ctx* ctx) {
+  const int slots = static_cast<int>(ctx->prof_names.size());
+  if (slots == 0 || ctx->prof_events.empty()) return;
+  cudaDeviceSynchronize();
+  const size_t per = static_cast<size_t>(slots) + 1;
+  for (size_t s0 = 0; s0 + per <= ctx->prof_events.size(); s0 += per) {
+    for (int i = 0; i < slots; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ctx->prof_events[s0 + i], ctx->prof_events[s0 + i + 1]) == cudaSuccess)
+        ctx->prof_sum_ms[i] += ms;
+    }
+    ctx->prof_samples++;
+  }
+  for (auto e : ctx->prof_events) cudaEventDestroy(e);
+  ctx->prof_events.clear();
 }
 
 int ensure_ident(nbe_ctx* ctx, int n) {
@@ -651,6 +673,59 @@ int ensure_ident(nbe_ctx* ctx, int n) {
 }
 
 size_t dtype_size(int dt) { return dt == NBE_F32 ? 4 : 2; }
+
+// Device-resident core of process_box: box_dev (3,size) in, disp_dev / vel_dev (3,size) out,
+// asynchronous on `stream`.  After subbox s has been enqueued `after(s)` is called (used by the
+// host wrapper to overlap the copy-back).
+template <class After>
+int process_box_core(nbe_ctx* ctx, const void* box_dev, int in_dtype, const int32_t size[3], const int32_t crop[3],
+                     const int32_t plen[3], const int32_t* crop_idx, const int32_t* add_idx0, int sub_first,
+                     int sub_count, float Dz, float vel_fac, void* disp_dev, void* vel_dev, int out_dtype,
+                     cudaStream_t st, After after) {
+  const int64_t S0 = size[0], S1 = size[1], S2 = size[2];
+  int rc;
+  const int per = plen[0] + plen[1] + plen[2];
+  const size_t idx_bytes = static_cast<size_t>(sub_count) * per * sizeof(int32_t);
+  if ((rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_idx), &ctx->idx_cap, idx_bytes))) return rc;
+  CK(cudaMemcpyAsync(ctx->d_idx, crop_idx + static_cast<size_t>(sub_first) * per, idx_bytes, cudaMemcpyHostToDevice, st));
+  Plan* P = nullptr;
+  if ((rc = build_plan(ctx, plen, 1, &P))) return rc;
+  const size_t es = dtype_size(out_dtype);
+  for (int s = 0; s < sub_count; ++s) {
+    const int32_t* ai = add_idx0 + static_cast<size_t>(sub_first + s) * 3;
+    const int32_t* di = ctx->d_idx + static_cast<size_t>(s) * per;
+    PackArgs pk{};
+    pk.src = box_dev; pk.src_dtype = in_dtype; pk.src_sc = S0 * S1 * S2; pk.src_sd = S1 * S2; pk.src_sh = S2;
+    pk.idx_d = di; pk.idx_h = di + plen[0]; pk.idx_w = di + plen[0] + plen[1];
+    pk.in_norm = Dz / 6.0f;
+    FinalArgs fa{};
+    fa.src = box_dev; fa.src_dtype = in_dtype; fa.src_sc = pk.src_sc; fa.src_sd = pk.src_sd; fa.src_sh = pk.src_sh;
+    fa.idx_d = pk.idx_d + 48; fa.idx_h = pk.idx_h + 48; fa.idx_w = pk.idx_w + 48;
+    const size_t base = (static_cast<size_t>(ai[0]) * S1 + ai[1]) * S2 + ai[2];
+    fa.disp = static_cast<uint8_t*>(disp_dev) + base * es;
+    fa.vel = ctx->vel ? static_cast<uint8_t*>(vel_dev) + base * es : nullptr;
+    fa.out_dtype = out_dtype; fa.mid_dtype = in_dtype; fa.o_sc = S0 * S1 * S2; fa.o_sd = S1 * S2; fa.o_sh = S2;
+    fa.in_norm = pk.in_norm; fa.six = 6.0f; fa.dx_norm = vel_fac * 6.0f; fa.x0_norm = vel_fac * 6.0f / Dz;
+    if ((rc = run_sample(ctx, P, 0, pk, fa, st))) return rc;
+    if ((rc = after(s))) return rc;
+  }
+  return NBE_OK;
+}
+
+int check_box_args(nbe_ctx* ctx, const void* in, const int32_t* size, const int32_t* crop, const int32_t* plen,
+                          const int32_t* crop_idx, const int32_t* add_idx0, const void* disp, const void* vel,
+                          int sub_count, int in_dtype, int out_dtype) {
+  if (!ctx->have_params) return fail(ctx, NBE_ERR_STATE, "process_box before nbe_set_params");
+  if (ctx->mod_batch != 1) return fail(ctx, NBE_ERR_STATE, "process_box needs weights modulated for one sample");
+  if (!in || !size || !crop || !plen || !crop_idx || !add_idx0 || !disp || sub_count < 0)
+    return fail(ctx, NBE_ERR_ARG, "null argument");
+  if (ctx->vel && !vel) return fail(ctx, NBE_ERR_ARG, "velocity model: velocity output required");
+  if (in_dtype < 0 || in_dtype > 2 || out_dtype < 0 || out_dtype > 2) return fail(ctx, NBE_ERR_ARG, "bad dtype");
+  for (int d = 0; d < 3; ++d)
+    if (plen[d] - crop[d] != 96) return fail(ctx, NBE_ERR_ARG, "padding must be 48 per side (the models hard-code the 48-voxel crop)");
+  return NBE_OK;
+}
+
 
 }  // namespace
 
@@ -877,76 +952,86 @@ int nbe_forward(nbe_ctx* ctx, const void* x_dev, int in_dtype, int batch, const 
   return NBE_OK;
 }
 
+int nbe_process_box_dev(nbe_ctx* ctx, const void* box_dev, int in_dtype, const int32_t size[3], const int32_t crop[3],
+                        const int32_t plen[3], const int32_t* crop_idx, const int32_t* add_idx0, int sub_first,
+                        int sub_count, float Dz, float vel_fac, void* disp_dev, void* vel_dev, int out_dtype,
+                        void* stream) {
+  if (!ctx) return NBE_ERR_ARG;
+  int rc = check_box_args(ctx, box_dev, size, crop, plen, crop_idx, add_idx0, disp_dev, vel_dev, sub_count, in_dtype, out_dtype);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  return process_box_core(ctx, box_dev, in_dtype, size, crop, plen, crop_idx, add_idx0, sub_first, sub_count, Dz,
+                          vel_fac, disp_dev, vel_dev, out_dtype, static_cast<cudaStream_t>(stream),
+                          [](int) { return NBE_OK; });
+}
+
 int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32_t size[3], const int32_t crop[3],
                     const int32_t plen[3], const int32_t* crop_idx, const int32_t* add_idx0, int sub_first,
                     int sub_count, float Dz, float vel_fac, void* disp_host, void* vel_host, int out_dtype) {
   if (!ctx) return NBE_ERR_ARG;
-  if (!ctx->have_params) return fail(ctx, NBE_ERR_STATE, "nbe_process_box before nbe_set_params");
-  if (ctx->mod_batch != 1) return fail(ctx, NBE_ERR_STATE, "nbe_process_box needs weights modulated for one sample");
-  if (!in_host || !size || !crop || !plen || !crop_idx || !add_idx0 || !disp_host || sub_count < 0)
-    return fail(ctx, NBE_ERR_ARG, "null argument");
-  if (ctx->vel && !vel_host) return fail(ctx, NBE_ERR_ARG, "velocity model: vel_host required");
-  if (in_dtype < 0 || in_dtype > 2 || out_dtype < 0 || out_dtype > 2) return fail(ctx, NBE_ERR_ARG, "bad dtype");
-  for (int d = 0; d < 3; ++d)
-    if (plen[d] - crop[d] != 96) return fail(ctx, NBE_ERR_ARG, "padding must be 48 per side (models hard-code the 48-voxel crop)");
+  int rc = check_box_args(ctx, in_host, size, crop, plen, crop_idx, add_idx0, disp_host, vel_host, sub_count, in_dtype, out_dtype);
+  if (rc) return rc;
   if (sub_count == 0) return NBE_OK;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->own_stream, cs = ctx->copy_stream;
   const int64_t S0 = size[0], S1 = size[1], S2 = size[2];
   const size_t in_bytes = static_cast<size_t>(3) * S0 * S1 * S2 * dtype_size(in_dtype);
   const size_t out_bytes = static_cast<size_t>(3) * S0 * S1 * S2 * dtype_size(out_dtype);
-  int rc;
   if ((rc = ensure(ctx, &ctx->d_box, &ctx->box_cap, in_bytes))) return rc;
   if ((rc = ensure(ctx, &ctx->d_disp, &ctx->out_cap, out_bytes))) return rc;
   if (ctx->vel && (rc = ensure(ctx, &ctx->d_velo, &ctx->velo_cap, out_bytes))) return rc;
-  const int per = plen[0] + plen[1] + plen[2];
-  const size_t idx_bytes = static_cast<size_t>(sub_count) * per * sizeof(int32_t);
-  if ((rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_idx), &ctx->idx_cap, idx_bytes))) return rc;
-  CK(cudaMemcpyAsync(ctx->d_idx, crop_idx + static_cast<size_t>(sub_first) * per, idx_bytes, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->d_box, in_host, in_bytes, cudaMemcpyHostToDevice, st));
-  Plan* P = nullptr;
-  if ((rc = build_plan(ctx, plen, 1, &P))) return rc;
   const size_t es = dtype_size(out_dtype);
   cudaEvent_t done;
   CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-  for (int s = 0; s < sub_count; ++s) {
-    const int32_t* ai = add_idx0 + static_cast<size_t>(sub_first + s) * 3;
-    const int32_t* di = ctx->d_idx + static_cast<size_t>(s) * per;
-    PackArgs pk{};
-    pk.src = ctx->d_box; pk.src_dtype = in_dtype; pk.src_sc = S0 * S1 * S2; pk.src_sd = S1 * S2; pk.src_sh = S2;
-    pk.idx_d = di; pk.idx_h = di + plen[0]; pk.idx_w = di + plen[0] + plen[1];
-    pk.in_norm = Dz / 6.0f;
-    FinalArgs fa{};
-    fa.src = ctx->d_box; fa.src_dtype = in_dtype; fa.src_sc = pk.src_sc; fa.src_sd = pk.src_sd; fa.src_sh = pk.src_sh;
-    fa.idx_d = pk.idx_d + 48; fa.idx_h = pk.idx_h + 48; fa.idx_w = pk.idx_w + 48;
-    const size_t base = (static_cast<size_t>(ai[0]) * S1 + ai[1]) * S2 + ai[2];
-    fa.disp = static_cast<uint8_t*>(ctx->d_disp) + base * es;
-    fa.vel = ctx->vel ? static_cast<uint8_t*>(ctx->d_velo) + base * es : nullptr;
-    fa.out_dtype = out_dtype; fa.mid_dtype = in_dtype; fa.o_sc = S0 * S1 * S2; fa.o_sd = S1 * S2; fa.o_sh = S2;
-    fa.in_norm = pk.in_norm; fa.six = 6.0f; fa.dx_norm = vel_fac * 6.0f; fa.x0_norm = vel_fac * 6.0f / Dz;
-    if ((rc = run_sample(ctx, P, 0, pk, fa, st))) { cudaEventDestroy(done); return rc; }
-    // paste: copy the owned block back (rows of crop[2] elements) while the next subbox computes
+  // Copy-back policy: consecutive subboxes sharing a D anchor form a run; when a run tiles the
+  // whole (H, W) plane the finished D-slab is contiguous per channel and goes back as one large
+  // copy per channel, otherwise each owned block is pasted with a strided 3-D copy.
+  const bool tiles_hw = crop[1] > 0 && crop[2] > 0 && S1 % crop[1] == 0 && S2 % crop[2] == 0;
+  const int run_full = tiles_hw ? static_cast<int>((S1 / crop[1]) * (S2 / crop[2])) : -1;
+  int run_start = 0;
+  auto flush_run = [&](int s_end) -> int {      // subboxes [run_start, s_end] are enqueued on st
     CK(cudaEventRecord(done, st));
     CK(cudaStreamWaitEvent(cs, done, 0));
+    const int n_run = s_end - run_start + 1;
+    const int32_t* a0 = add_idx0 + static_cast<size_t>(sub_first + run_start) * 3;
     for (int f = 0; f < (ctx->vel ? 2 : 1); ++f) {
       uint8_t* dsrc = static_cast<uint8_t*>(f == 0 ? ctx->d_disp : ctx->d_velo);
       uint8_t* hdst = static_cast<uint8_t*>(f == 0 ? disp_host : vel_host);
       for (int c = 0; c < 3; ++c) {
-        cudaMemcpy3DParms p3 = {};
         const size_t choff = static_cast<size_t>(c) * S0 * S1 * S2 * es;
-        p3.srcPtr = make_cudaPitchedPtr(dsrc + choff, S2 * es, S2, S1);
-        p3.dstPtr = make_cudaPitchedPtr(hdst + choff, S2 * es, S2, S1);
-        p3.srcPos = make_cudaPos(static_cast<size_t>(ai[2]) * es, ai[1], ai[0]);
-        p3.dstPos = p3.srcPos;
-        p3.extent = make_cudaExtent(static_cast<size_t>(crop[2]) * es, crop[1], crop[0]);
-        p3.kind = cudaMemcpyDeviceToHost;
-        CK(cudaMemcpy3DAsync(&p3, cs));
+        if (n_run == run_full) {
+          const size_t off = choff + static_cast<size_t>(a0[0]) * S1 * S2 * es;
+          CK(cudaMemcpyAsync(hdst + off, dsrc + off, static_cast<size_t>(crop[0]) * S1 * S2 * es, cudaMemcpyDeviceToHost, cs));
+        } else {
+          for (int s = run_start; s <= s_end; ++s) {
+            const int32_t* ai = add_idx0 + static_cast<size_t>(sub_first + s) * 3;
+            cudaMemcpy3DParms p3 = {};
+            p3.srcPtr = make_cudaPitchedPtr(dsrc + choff, S2 * es, S2, S1);
+            p3.dstPtr = make_cudaPitchedPtr(hdst + choff, S2 * es, S2, S1);
+            p3.srcPos = make_cudaPos(static_cast<size_t>(ai[2]) * es, ai[1], ai[0]);
+            p3.dstPos = p3.srcPos;
+            p3.extent = make_cudaExtent(static_cast<size_t>(crop[2]) * es, crop[1], crop[0]);
+            p3.kind = cudaMemcpyDeviceToHost;
+            CK(cudaMemcpy3DAsync(&p3, cs));
+          }
+        }
       }
     }
-  }
+    run_start = s_end + 1;
+    return NBE_OK;
+  };
+  rc = process_box_core(ctx, ctx->d_box, in_dtype, size, crop, plen, crop_idx, add_idx0, sub_first, sub_count, Dz, vel_fac,
+                        ctx->d_disp, ctx->d_velo, out_dtype, st, [&](int s) -> int {
+                          const int32_t* ai = add_idx0 + static_cast<size_t>(sub_first + s) * 3;
+                          const bool last = s + 1 == sub_count;
+                          const bool run_ends = last || (ai + 3)[0] != ai[0] || (s - run_start + 1) == run_full;
+                          return run_ends ? flush_run(s) : NBE_OK;
+                        });
   cudaError_t e1 = cudaStreamSynchronize(st);
   cudaError_t e2 = cudaStreamSynchronize(cs);
   cudaEventDestroy(done);
+  if (rc) return rc;
   if (e1 != cudaSuccess) return fail(ctx, NBE_ERR_CUDA, "process_box: %s", cudaGetErrorString(e1));
   if (e2 != cudaSuccess) return fail(ctx, NBE_ERR_CUDA, "process_box copy: %s", cudaGetErrorString(e2));
   return NBE_OK;
@@ -961,16 +1046,24 @@ int64_t nbe_launch_count(nbe_ctx* ctx, int reset) {
 
 int nbe_set_profiling(nbe_ctx* ctx, int enable) {
   if (!ctx) return NBE_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  resolve_profile(ctx);
   ctx->profiling = enable != 0;
+  if (enable) {     // start a fresh accumulation
+    std::fill(ctx->prof_sum_ms.begin(), ctx->prof_sum_ms.end(), 0.0);
+    ctx->prof_samples = 0;
+  }
   return NBE_OK;
 }
 
 int nbe_get_profile(nbe_ctx* ctx, int cap, const char** names, float* ms, double* flops) {
   if (!ctx) return NBE_ERR_ARG;
-  const int n = static_cast<int>(std::min(ctx->prof_ms.size(), ctx->prof_names.size()));
+  cudaSetDevice(ctx->device);
+  resolve_profile(ctx);
+  const int n = static_cast<int>(ctx->prof_names.size());
   for (int i = 0; i < n && i < cap; ++i) {
     if (names) names[i] = ctx->prof_names[i].c_str();
-    if (ms) ms[i] = ctx->prof_ms[i];
+    if (ms) ms[i] = ctx->prof_samples ? static_cast<float>(ctx->prof_sum_ms[i] / ctx->prof_samples) : 0.f;
     if (flops) flops[i] = ctx->prof_flops[i];
   }
   return n;

@@ -12,7 +12,7 @@ namespace nbe {
 // Every spin in this library is bounded: a pipeline bug must surface as a CUDA error
 // (trap), never as a hung GPU.
 #ifndef NBE_WAIT_TIMEOUT_NS
-#define NBE_WAIT_TIMEOUT_NS 4000000000ull   // 4 s: two orders of magnitude above the longest launch
+#define NBE_WAIT_TIMEOUT_NS 2000000000ull   // 2 s: far above the longest launch (tens of ms)
 #endif
 __device__ __forceinline__ uint64_t global_timer_ns() {
   uint64_t t;
@@ -56,10 +56,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > 4096u) {
+    if (++spins > 1024u) {
       const uint64_t now = global_timer_ns();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > NBE_WAIT_TIMEOUT_NS) __trap();
+      else if (now - t0 > NBE_WAIT_TIMEOUT_NS || spins > (1u << 26)) __trap();
     }
   }
 }
@@ -109,6 +109,26 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same, issued only by threads with `issue` != 0, with the predicate inside the asm so that the
+// surrounding C++ control flow stays warp-uniform (operands remain in uniform registers).
+__device__ __forceinline__ void umma_f16_pred(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(issue)
       : "memory");
 }
 // mbarrier arrive once all previously issued tcgen05.mma of this thread have completed.
