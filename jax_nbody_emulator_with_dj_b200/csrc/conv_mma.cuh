@@ -183,6 +183,21 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Accumulators start at zero and are re-zeroed by the epilogue after each read, so every MMA
+  // accumulates and the launch may order its terms freely (small lo-products first: the tensor
+  // core truncates on accumulation, and truncation error scales with the running sum).
+  if (warp >= 4) {
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    if constexpr (DC >= 32) {
+      for (int c = 0; c < Cfg::kNBuf * TM * DC; c += 32) tmem_st32_zero(lane_base + c);
+    } else {
+      for (int c = 0; c < Cfg::kNBuf * TM * DC; c += 16) tmem_st16_zero(lane_base + c);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   auto decode = [&](long long item, int& par, int& w0, int& h0, int& d0) {
     const int tw = static_cast<int>(item % tiles_w); item /= tiles_w;
@@ -267,8 +282,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
           mbar_wait(&b_full[sb], pb);
           tc_fence_after();
           const uint32_t b_lo = ((smem_u32(b_smem + sb * Cfg::kBStage) & 0x3FFFFu) >> 4) | (1u << 16);
-          const uint32_t first = (g | j) == 0 ? 0u : 1u;
-          {
+          if (elect_one()) {
 #pragma unroll
             for (int t = 0; t < TM; ++t) {
               const uint32_t d_tile = tmem_u + (buf * TM + t) * DC;
@@ -277,30 +291,33 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
 #pragma unroll
                 for (int o = 0; o < 3; ++o)
                   if (o < n_ops)
-                    umma_f16_pred(d_tile + op_d[o], (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + op_a[o] + a_row),
+                    umma_f16(d_tile + op_d[o], (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + op_a[o] + a_row),
                                   (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + op_b[o]), op_i[o],
-                                  o == 0 ? first : 1u, issuer);
+                                  1u);
               } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
 #pragma unroll
                   for (int o = 0; o < 3; ++o)
                     if (o < n_ops)
-                      umma_f16_pred(d_tile + op_d[o],
+                      umma_f16(d_tile + op_d[o],
                                     (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + op_a[o] + a_row + 2u * k),
                                     (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + op_b[o] + 2u * k), op_i[o],
-                                    (k | o) == 0 ? first : 1u, issuer);
+                                    1u);
                 }
               }
             }
-            umma_commit_pred(&b_empty[sb], issuer);
+            umma_commit(&b_empty[sb]);
           }
+          __syncwarp();
           if (++sb == Cfg::kNB) { sb = 0; pb ^= 1; }
         }
-        umma_commit_pred(&a_empty[sa], issuer);
+        if (elect_one()) umma_commit(&a_empty[sa]);
+        __syncwarp();
         if (++sa == Cfg::kNA) { sa = 0; pa ^= 1; }
       }
-      umma_commit_pred(&acc_full[buf], issuer);
+      if (elect_one()) umma_commit(&acc_full[buf]);
+      __syncwarp();
       if (++buf == Cfg::kNBuf) { buf = 0; pacc ^= 1; }
     }
   } else if (warp >= 4) {
@@ -323,6 +340,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
           uint32_t v[16];
           tmem_ld16(taddr, v);
           tmem_ld_wait();
+          tmem_st16_zero(taddr);
           if (valid) {
             const int64_t sidx = static_cast<int64_t>(fa.idx_d[d0]) * fa.src_sd +
                                  static_cast<int64_t>(fa.idx_h[h]) * fa.src_sh + fa.idx_w[w];
@@ -359,6 +377,8 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
             tmem_ld32(taddr + c, y);
             if (vel) tmem_ld32(taddr + cout + c, dy);
             tmem_ld_wait();
+            tmem_st32_zero(taddr + c);
+            if (vel) tmem_st32_zero(taddr + cout + c);
             uint32_t ph[16], pl[16], pd[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
@@ -391,6 +411,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
           }
         }
       }
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
       if (++buf == Cfg::kNBuf) { buf = 0; pacc ^= 1; }

@@ -443,7 +443,11 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
 
       int ng = 0;
       bool bad = false;
-      auto push = [&](const GroupDesc& G) { if (ng < kMaxGroups) H.G.g[ng++] = G; else bad = true; };
+      // lo-product groups are issued before the main groups (see conv_mma.cuh: truncating
+      // accumulation), so collect them separately
+      std::vector<GroupDesc> g_lo, g_main;
+      int cur_kind = 0;
+      auto push = [&](const GroupDesc& G) { (cur_kind == 1 ? g_lo : g_main).push_back(G); };
       const int nkind = (vel && split) ? 2 : 1;
       const ActBuf& OB = P->act[s.out_act];
       // tile space = output voxels, except for the up-sampling conv (input voxels)
@@ -518,6 +522,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           G.dw = static_cast<int8_t>(sc.crop + p.off + dw_); G.dh = static_cast<int8_t>(sc.crop + p.off + dh_);
           G.dd = static_cast<int8_t>(sc.crop + p.off + dd_);
           G.brow0 = tile0 * ii.nrs; G.brow_step = ii.nrs;
+          cur_kind = k16 ? 0 : kind;
           fill_ops(G, kind, sc, par);
           if (G.a_map[0] < 0 || (G.n_a == 2 && G.a_map[1] < 0)) bad = true;
           push(G);
@@ -545,6 +550,8 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           H.flops += 2.0 * ly.cout * ly.cin * vout * m;
         }
       }
+      for (const auto& G : g_lo) { if (ng < kMaxGroups) H.G.g[ng++] = G; else bad = true; }
+      for (const auto& G : g_main) { if (ng < kMaxGroups) H.G.g[ng++] = G; else bad = true; }
       if (bad) { delete P; return fail(ctx, NBE_ERR_STATE, "launch %s: too many groups / tensor maps", s.name.c_str()); }
       H.G.n_groups = ng;
       Lc.cout = s.cout; Lc.vel = vel ? 1 : 0; Lc.act = 1;

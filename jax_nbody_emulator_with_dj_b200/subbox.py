@@ -110,6 +110,7 @@ class SubboxProcessor:
             self.compute_vel = False
         self._tables = None
         self._out = None           # cached pinned output buffers
+        self._out_range = None
         self._pinned_in = None     # (ptr, nbytes) of the host input currently page-locked
 
     def _outputs(self, shape, out_np):
@@ -118,6 +119,7 @@ class SubboxProcessor:
             dis = _pinned_zeros(shape, out_np)
             vel = _pinned_zeros(shape, out_np) if self.compute_vel else (None, None)
             self._out = (key, dis, vel)
+            self._out_range = None
         return self._out[1][1], self._out[2][1]
 
     def _pin_input(self, box):
@@ -179,6 +181,13 @@ class SubboxProcessor:
 
         shape = (cfg.in_chan,) + tuple(cfg.size)
         dis, vel = self._outputs(shape, out_np)
+        # voxels not owned by [lo, hi) must read zero: the cached buffers only need clearing when
+        # the owned range differs from the previous call's (owned blocks are always overwritten)
+        if self._out_range not in (None, (lo, hi)):
+            dis.fill(0)
+            if vel is not None:
+                vel.fill(0)
+        self._out_range = (lo, hi)
         self._pin_input(box)
         bar = None
         if show_progress:

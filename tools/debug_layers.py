@@ -52,7 +52,8 @@ for aid, name in enumerate(ACTS):
         print('%-18s x %.3e' % (name, rel_l2(got, rx)), flush=True)
         continue
     got = hi + (rd(1) if prec == 'split' else 0)
-    msg = '%-18s %s x %.3e' % (name, (d, h, w, c), rel_l2(got, rx))
+    proj = float(((got - rx) * rx).sum() / (rx * rx).sum())
+    msg = '%-18s %s x %.3e proj %+.2e' % (name, (d, h, w, c), rel_l2(got, rx), proj)
     if vel:
         msg += '  dx %.3e' % rel_l2(rd(2), rdx[0].permute(1, 2, 3, 0).numpy())
     print(msg, flush=True)

@@ -22,33 +22,53 @@ def field(shape, seed=1234):
     return np.random.default_rng(seed).standard_normal(shape, dtype=np.float32)
 
 
-def run(x, z, Om, style=True, vel=True, params=P):
+def run(x, z, Om, style=True, vel=True, params=P, dtype=torch.float64):
     z = np.atleast_1d(np.asarray(z, dtype=np.float64)); Om = np.atleast_1d(np.asarray(Om, dtype=np.float64))
     Dz = oc.growth_factor(z, Om).astype(np.float32).astype(np.float64)   # the product works from fp32 scalars
     vf = oc.vel_norm(z, Om).astype(np.float32).astype(np.float64)
-    out = Net(style, vel, torch.float64).forward(params, x, Om.astype(np.float32).astype(np.float64), Dz, vf)
+    out = Net(style, vel, dtype).forward(params, x, Om.astype(np.float32).astype(np.float64), Dz, vf)
     return [o.numpy() for o in (out if vel else [out])]
 
 
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a, np.float64) - b) / np.linalg.norm(b))
+
+
+def with_cond(x, z, Om, **meta):
+    """fp64 oracle outputs plus the conditioning of the case: how far the SAME oracle run in
+    plain fp32 lands from fp64.  The velocity depends discontinuously on the signs of the
+    pre-activations (LeakyReLU tangent rule), so for some inputs a single mask flip in a small
+    layer moves it by > 1e-3 whatever the implementation; cond_vel measures that."""
+    d, v = run(x, z, Om)
+    d32, v32 = run(x, z, Om, dtype=torch.float32)
+    return dict(disp=d, vel=v, cond_disp=rel(d32, d), cond_vel=rel(v32, v), z=z, Om=Om, **meta)
+
+
 def g_n104():
-    d, v = run(field((1, 3, 104, 104, 104)), 0.5, 0.3)
-    return dict(disp=d, vel=v, z=0.5, Om=0.3, seed=1234, N=104)
+    return with_cond(field((1, 3, 104, 104, 104)), 0.5, 0.3, seed=1234, N=104)
 
 
 def g_batch2():
-    z, Om = [0.0, 2.0], [0.1, 0.5]
-    d, v = run(field((2, 3, 104, 104, 104), 77), z, Om)
-    return dict(disp=d, vel=v, z=z, Om=Om, seed=77, N=104)
+    return with_cond(field((2, 3, 104, 104, 104), 77), [0.0, 2.0], [0.1, 0.5], seed=77, N=104)
 
 
 def g_noncubic():
-    d, v = run(field((1, 3, 104, 112, 120), 5), 1.0, 0.25)
-    return dict(disp=d, vel=v, z=1.0, Om=0.25, seed=5, shape=(104, 112, 120))
+    """well-conditioned non-cubic case: first seed whose fp32/fp64 oracle runs agree to 1e-4"""
+    for seed in (6, 7, 8, 9, 10, 11):
+        r = with_cond(field((1, 3, 104, 112, 120), seed), 1.0, 0.25, seed=seed, shape=(104, 112, 120))
+        print('noncubic seed', seed, 'cond_vel %.2e' % r['cond_vel'], flush=True)
+        if r['cond_vel'] < 1e-4:
+            return r
+    raise SystemExit('no well-conditioned seed found')
+
+
+def g_illcond():
+    """the ill-conditioned twin (seed 5): plain fp32 is 1.5e-3 away from fp64 in velocity"""
+    return with_cond(field((1, 3, 104, 112, 120), 5), 1.0, 0.25, seed=5, shape=(104, 112, 120))
 
 
 def g_n128():
-    d, v = run(field((1, 3, 128, 128, 128), 9), 0.5, 0.3)
-    return dict(disp=d, vel=v, z=0.5, Om=0.3, seed=9, N=128)
+    return with_cond(field((1, 3, 128, 128, 128), 9), 0.5, 0.3, seed=9, N=128)
 
 
 def g_box():
@@ -62,7 +82,19 @@ def g_box():
     return dict(disp=d, vel=v, z=z, Om=Om, seed=31, size=size, ndiv=ndiv)
 
 
-ALL = dict(n104=g_n104, batch2=g_batch2, noncubic=g_noncubic, box=g_box, n128=g_n128)
+def g_box64():
+    # the reference tests' standard box: 64^3, ndiv 2 => crop 32, padded 128^3 (pad 48 > crop)
+    size, ndiv = (64, 64, 64), (2, 2, 2)
+    box = field((3,) + size, 64)
+    z, Om = 0.5, 0.3
+    Dz = np.float64(np.float32(oc.growth_factor(z, Om))); vf = np.float64(np.float32(oc.vel_norm(z, Om)))
+    net = Net(True, True, torch.float32)
+    f = lambda x: [o.numpy() for o in net.forward(P, x, np.float64(np.float32(Om)), Dz, vf)]
+    d, v = osb.process_box(f, box, size, ndiv, dtype=np.float32, output_dtype=np.float32)
+    return dict(disp=d.astype(np.float32), vel=v.astype(np.float32), z=z, Om=Om, seed=64, size=size, ndiv=ndiv)
+
+
+ALL = dict(illcond=g_illcond, box64=g_box64, n104=g_n104, batch2=g_batch2, noncubic=g_noncubic, box=g_box, n128=g_n128)
 for name in (sys.argv[1:] or list(ALL)):
     t = time.time()
     r = ALL[name]()
