@@ -11,7 +11,7 @@ import subprocess
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnbe_b200.so")
+LIB_PATH = os.environ.get("NBE_LIB") or os.path.join(HERE, "libnbe_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]

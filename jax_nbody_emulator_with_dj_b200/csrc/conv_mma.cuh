@@ -39,12 +39,12 @@ struct MmaOp {
 struct GroupDesc {
   int16_t a_map[2];   // tensor-map index of operand 0 / 1 (-1: absent)
   int8_t n_a;         // operand blocks to load (1 or 2)
-  int8_t ntaps;       // taps along h served from the block (1 or 3)
+  int8_t ntaps;       // taps served from the block: 1, 3 (kh) or 9 (kw-major: j = kw*3 + kh)
   int8_t kc16;        // 1: 16-channel rows (32 B, SWIZZLE_32B); 0: 64-channel rows (128 B)
   int8_t n_ops;
   int16_t c0;         // channel coordinate of the box
   int8_t dw, dh, dd;  // block origin relative to the tile origin
-  int8_t pad_;
+  int8_t pitch;       // rows per h-line of the block: 8, or 10 (w-halo'd "wide" block, kw taps by row shift)
   int32_t brow0;      // B row of tap 0
   int32_t brow_step;  // B rows between consecutive taps
   MmaOp ops[3];
@@ -119,8 +119,8 @@ __device__ __forceinline__ void store_from_f32(void* p, int64_t i, int dtype, fl
 
 template <int NRS, int DC, int TM>
 struct ConvCfg {
-  static constexpr int kRows = (16 * TM + 2) * 8;          // rows of one activation block
-  static constexpr int kABlk = kRows * 128;                // bytes (64-channel rows)
+  static constexpr int kHRows = 16 * TM + 2;               // h-lines of one activation block
+  static constexpr int kABlk = (kHRows * 10 * 128 + 1023) / 1024 * 1024;   // bytes, wide 64-channel block
   static constexpr int kAStage = 2 * kABlk;
   static constexpr int kBStage = NRS * 128;
   static constexpr int kNA = (TM == 1) ? 3 : 2;
@@ -136,6 +136,12 @@ struct ConvCfg {
   static_assert(kNB >= 2, "not enough shared memory for the B ring");
   static_assert(kColsRaw <= 512, "TMEM overflow");
 };
+
+// 0: base_offset field left 0 for row-shifted operand starts; 1: base_offset = (addr >> 7) & 7
+#ifndef NBE_BASE_OFFSET
+#define NBE_BASE_OFFSET 0
+#endif
+constexpr bool kBaseOffsetMode = NBE_BASE_OFFSET != 0;
 
 template <int NRS, int DC, int TM, bool FINAL>
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -217,7 +223,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
         decode(item, par, w0, h0, d0);
         for (int g = 0; g < n_groups; ++g) {
           const GroupDesc& G = gt.g[g];
-          const uint32_t blk = G.kc16 ? Cfg::kRows * 32 : Cfg::kABlk;
+          const uint32_t blk = static_cast<uint32_t>(Cfg::kHRows) * G.pitch * (G.kc16 ? 32u : 128u);
           mbar_wait(&a_empty[s], ph ^ 1);
           mbar_expect_tx(&a_full[s], blk * G.n_a);
           for (int q = 0; q < G.n_a; ++q)
@@ -253,7 +259,6 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     // The whole warp runs this loop with warp-uniform control flow and values (so they stay in
     // uniform registers); lane 0 alone issues tcgen05.mma / tcgen05.commit.
     constexpr uint32_t idesc_base = umma_idesc_f16(128, 0, false);
-    const uint32_t issuer = lane == 0 ? 1u : 0u;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0, buf = 0, pacc = 0;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -264,9 +269,13 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
         const int ntaps = G.ntaps, n_ops = G.n_ops;
         const bool k16 = G.kc16 != 0;
         const uint32_t rowb = k16 ? 32u : 128u;
-        const uint32_t sbo16 = rowb >> 1;                       // (8 rows * rowb) >> 4
+        const uint32_t row16 = rowb >> 4;                       // one row in 16-byte units
+        const uint32_t pitch = static_cast<uint32_t>(G.pitch);
+        const uint32_t sbo16 = pitch * row16;                   // h-line stride = 8-row group stride
+        const uint32_t bsbo16 = 8u * row16;                     // B stages are dense
         // upper descriptor word: SBO | version | layout
         const uint32_t desc_hi = sbo16 | (1u << 14) | ((k16 ? 6u : 2u) << 29);
+        const uint32_t bdesc_hi = bsbo16 | (1u << 14) | ((k16 ? 6u : 2u) << 29);
         uint32_t op_a[3], op_b[3], op_d[3], op_i[3];
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
@@ -286,14 +295,20 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
 #pragma unroll
             for (int t = 0; t < TM; ++t) {
               const uint32_t d_tile = tmem_u + (buf * TM + t) * DC;
-              const uint32_t a_row = static_cast<uint32_t>(t * 16 + j) * sbo16;
+              const uint32_t kw = ntaps == 9 ? static_cast<uint32_t>(j) / 3u : 0u;
+              const uint32_t kh = ntaps == 9 ? static_cast<uint32_t>(j) % 3u : static_cast<uint32_t>(j);
+              const uint32_t a_row = (static_cast<uint32_t>(t * 16) + kh) * sbo16 + kw * row16;
+              // kw taps start at a row that is not a multiple of the 8-row swizzle atom.  Measured on
+              // B200: the MMA unit swizzles on absolute smem address bits (like TMA), so the plain
+              // shifted start with base_offset = 0 is correct; setting base_offset = (addr>>7)&7 is
+              // WRONG (NBE_BASE_OFFSET=1 reproduces that experiment).
+              const uint32_t a_hi = desc_hi | (kBaseOffsetMode ? (((a_lo + a_row) >> 3) & 7u) << 17 : 0u);
               if (k16) {
 #pragma unroll
                 for (int o = 0; o < 3; ++o)
                   if (o < n_ops)
-                    umma_f16(d_tile + op_d[o], (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + op_a[o] + a_row),
-                                  (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + op_b[o]), op_i[o],
-                                  1u);
+                    umma_f16(d_tile + op_d[o], (static_cast<uint64_t>(a_hi) << 32) | (a_lo + op_a[o] + a_row),
+                             (static_cast<uint64_t>(bdesc_hi) << 32) | (b_lo + op_b[o]), op_i[o], 1u);
               } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -301,9 +316,8 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
                   for (int o = 0; o < 3; ++o)
                     if (o < n_ops)
                       umma_f16(d_tile + op_d[o],
-                                    (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + op_a[o] + a_row + 2u * k),
-                                    (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + op_b[o] + 2u * k), op_i[o],
-                                    1u);
+                               (static_cast<uint64_t>(a_hi) << 32) | (a_lo + op_a[o] + a_row + 2u * k),
+                               (static_cast<uint64_t>(bdesc_hi) << 32) | (b_lo + op_b[o] + 2u * k), op_i[o], 1u);
                 }
               }
             }

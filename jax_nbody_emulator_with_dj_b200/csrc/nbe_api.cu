@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -30,7 +31,7 @@ enum ConvType { T_CONV3 = 0, T_SKIP1 = 1, T_DOWN = 2, T_UP = 3 };
 enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_COUNT };
 struct InstInfo { int nrs, dc, tm; bool fin; };
 const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32, 16, 2, true},
-                                 {128, 64, 2, false},  {64, 64, 2, false},   {256, 128, 2, false}};
+                                 {128, 64, 2, false},  {64, 64, 2, false},   {256, 128, 1, false}};
 
 // activation tensors of the net
 enum ActId {
@@ -94,6 +95,7 @@ struct nbe_ctx {
   bool have_params = false, premod = false, vel = true;
   float eps = 1e-8f;
   int precision = NBE_PREC_SPLIT;
+  bool wide = true;         // w-halo'd activation blocks serving 9 taps per load (NBE_WIDE=0 disables)
   std::vector<Layer> layers;
   std::map<std::string, int> lidx;
 
@@ -237,9 +239,10 @@ int build_static(nbe_ctx* ctx) {
       M.kc16 = k16; M.nrs = ii.nrs;
       const int k3 = ly.k * ly.k * ly.k;
       if (p.type == T_CONV3) {
+        // stage order (kd, kc, kind, kw, kh): the 9 taps of a (kd, kc, kind) group are consecutive
         for (int kd = 0; kd < 3; ++kd) for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw)
-          M.tap_tile[(kd * 3 + kh) * 3 + kw] = tb + ((kd * 3 + kw) * nkc * nk) * 3 + kh;
-        M.kc_stride = nk * 3; M.kind_stride = 3;
+          M.tap_tile[(kd * 3 + kh) * 3 + kw] = tb + (kd * nkc * nk) * 9 + kw * 3 + kh;
+        M.kc_stride = nk * 9; M.kind_stride = 9;
         tb += 27 * nkc * nk;
       } else if (p.type == T_SKIP1) {
         M.tap_tile[0] = tb; M.kc_stride = nk; M.kind_stride = 1; tb += nkc * nk;
@@ -315,7 +318,7 @@ int build_static(nbe_ctx* ctx) {
 // tensor maps
 // ----------------------------------------------------------------------------------------
 int make_act_map(nbe_ctx* ctx, CUtensorMap* m, const __half* base, int C, int W, int H, int D, int kc, int box_h,
-                 int par /* -1 or parity (a,b,c) of a stride-2 view */) {
+                 int par /* -1 or parity (a,b,c) of a stride-2 view */, int box_w = 8) {
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
                         static_cast<cuuint64_t>(D)};
   cuuint64_t str[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(C) * W * 2,
@@ -327,7 +330,7 @@ int make_act_map(nbe_ctx* ctx, CUtensorMap* m, const __half* base, int C, int W,
     dims[1] = W / 2; dims[2] = H / 2; dims[3] = D / 2;
     str[0] *= 2; str[1] *= 2; str[2] *= 2;
   }
-  cuuint32_t box[4] = {static_cast<cuuint32_t>(kc), 8u, static_cast<cuuint32_t>(box_h), 1u};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(kc), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1u};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(p), dims, str, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -428,13 +431,14 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
       const int box_h = 16 * ii.tm + 2;
       std::map<std::pair<const void*, int>, int> amap;
       int n_amap = 0;
+      int cur_box_w = 8;
       auto get_map = [&](const __half* ptr, int act, int par) -> int {
-        auto key = std::make_pair(static_cast<const void*>(ptr), par);
+        auto key = std::make_pair(static_cast<const void*>(ptr), par * 16 + cur_box_w);
         auto it = amap.find(key);
         if (it != amap.end()) return it->second;
         if (n_amap >= kMaxAMaps) return -1;
         const ActBuf& B = P->act[act];
-        if (make_act_map(ctx, &Lc.amap[n_amap], ptr, B.c, B.w, B.h, B.d, B.c == 16 ? 16 : 64, box_h, par)) return -1;
+        if (make_act_map(ctx, &Lc.amap[n_amap], ptr, B.c, B.w, B.h, B.d, B.c == 16 ? 16 : 64, box_h, par, cur_box_w)) return -1;
         amap[key] = n_amap;
         return n_amap++;
       };
@@ -522,6 +526,8 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           G.dw = static_cast<int8_t>(sc.crop + p.off + dw_); G.dh = static_cast<int8_t>(sc.crop + p.off + dh_);
           G.dd = static_cast<int8_t>(sc.crop + p.off + dd_);
           G.brow0 = tile0 * ii.nrs; G.brow_step = ii.nrs;
+          G.pitch = static_cast<int8_t>(ntaps == 9 ? 10 : 8);
+          cur_box_w = G.pitch;
           cur_kind = k16 ? 0 : kind;
           fill_ops(G, kind, sc, par);
           if (G.a_map[0] < 0 || (G.n_a == 2 && G.a_map[1] < 0)) bad = true;
@@ -530,9 +536,13 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
         const double m = vel ? ((k16 || false) ? 2.0 : 3.0) : 1.0;
         double vout = static_cast<double>(OB.d) * OB.h * OB.w;
         if (p.type == T_CONV3) {
-          for (int kd = 0; kd < 3; ++kd) for (int kw = 0; kw < 3; ++kw)
-            for (int q = 0; q < nkc; ++q) for (int kind = 0; kind < nk; ++kind)
-              mk(p.src[q], -1, kw, 0, kd, 3, tb + (((kd * 3 + kw) * nkc + q) * nk + kind) * 3, kind);
+          const bool wide = ctx->wide && !k16;
+          for (int kd = 0; kd < 3; ++kd)
+            for (int q = 0; q < nkc; ++q) for (int kind = 0; kind < nk; ++kind) {
+              const int t0 = tb + ((kd * nkc + q) * nk + kind) * 9;
+              if (wide) mk(p.src[q], -1, 0, 0, kd, 9, t0, kind);
+              else for (int kw = 0; kw < 3; ++kw) mk(p.src[q], -1, kw, 0, kd, 3, t0 + kw * 3, kind);
+            }
           H.flops += 2.0 * ly.cout * ly.cin * 27 * vout * m;
         } else if (p.type == T_SKIP1) {
           for (int q = 0; q < nkc; ++q) for (int kind = 0; kind < nk; ++kind)
@@ -609,7 +619,7 @@ cudaError_t launch_conv(int inst, const ConvLaunch* dl, const GroupTable& gt, co
     case I_FINAL: return launch_inst<32, 16, 2, true>(dl, gt, fa, grid, st);
     case I_128_64_2: return launch_inst<128, 64, 2, false>(dl, gt, fa, grid, st);
     case I_64_64_2: return launch_inst<64, 64, 2, false>(dl, gt, fa, grid, st);
-    case I_256_128_2: return launch_inst<256, 128, 2, false>(dl, gt, fa, grid, st);
+    case I_256_128_2: return launch_inst<256, 128, 1, false>(dl, gt, fa, grid, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -761,6 +771,7 @@ int nbe_create(nbe_ctx** out, int device) {
     return NBE_ERR_CUDA;
   }
   ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if (const char* e = getenv("NBE_WIDE")) ctx->wide = atoi(e) != 0;
   cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   *out = ctx;

@@ -41,7 +41,19 @@ def with_cond(x, z, Om, **meta):
     layer moves it by > 1e-3 whatever the implementation; cond_vel measures that."""
     d, v = run(x, z, Om)
     d32, v32 = run(x, z, Om, dtype=torch.float32)
-    return dict(disp=d, vel=v, cond_disp=rel(d32, d), cond_vel=rel(v32, v), z=z, Om=Om, **meta)
+    # the product's own arithmetic emulated on the CPU (fp16 hi+lo primal, fp16 tangent, fp32
+    # accumulate): how sensitive this input is at the ~22-bit primal precision the kernels carry
+    h = torch.float16
+    r1 = lambda t: t.to(h).to(t.dtype)
+    def r2(t):
+        a = t.to(h).to(t.dtype); return a + (t - a).to(h).to(t.dtype)
+    zz = np.atleast_1d(np.asarray(z, dtype=np.float64)); oo = np.atleast_1d(np.asarray(Om, dtype=np.float64))
+    Dz = oc.growth_factor(zz, oo).astype(np.float32).astype(np.float64)
+    vf = oc.vel_norm(zz, oo).astype(np.float32).astype(np.float64)
+    net = Net(True, True, torch.float32, ops=dict(xp=r2, wp=r2, xt=r1, wt=r1, dw=r1, dx=r1))
+    de, ve = [t.numpy() for t in net.forward(P, x, oo.astype(np.float32).astype(np.float64), Dz, vf)]
+    return dict(disp=d, vel=v, cond_disp=rel(d32, d), cond_vel=rel(v32, v), emu_disp=rel(de, d),
+                emu_vel=rel(ve, v), z=z, Om=Om, **meta)
 
 
 def g_n104():
@@ -94,9 +106,15 @@ def g_box64():
     return dict(disp=d.astype(np.float32), vel=v.astype(np.float32), z=z, Om=Om, seed=64, size=size, ndiv=ndiv)
 
 
+def cand(kind, seed):
+    if kind == 'noncubic':
+        return with_cond(field((1, 3, 104, 112, 120), seed), 1.0, 0.25, seed=seed, shape=(104, 112, 120))
+    return with_cond(field((1, 3, 128, 128, 128), seed), 0.5, 0.3, seed=seed, shape=(128, 128, 128))
+
+
 ALL = dict(illcond=g_illcond, box64=g_box64, n104=g_n104, batch2=g_batch2, noncubic=g_noncubic, box=g_box, n128=g_n128)
 for name in (sys.argv[1:] or list(ALL)):
     t = time.time()
-    r = ALL[name]()
+    r = cand(*name.split('_')[1:3][:1], int(name.split('_')[2])) if name.startswith('cand_') else ALL[name]()
     np.savez_compressed(os.path.join(OUT, f'{name}.npz'), **r)
     print(name, 'done in %.0fs' % (time.time() - t), flush=True)
