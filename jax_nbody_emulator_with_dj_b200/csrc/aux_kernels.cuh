@@ -24,7 +24,7 @@ struct EmitRule {
   int8_t kind;        // tile-kind offset (x kind_stride tiles)
   int16_t row_base;   // row of output channel 0 inside the B stage
   int16_t kcol;       // column offset (16-channel rows only)
-  int16_t pad_;
+  int16_t alt_kd1;    // added to row_base for the taps with kd == 1 of a 3^3 conv (see acc3 layout)
 };
 
 struct LayerMeta {
@@ -113,16 +113,21 @@ modulate_kernel(const LayerMeta* __restrict__ metas, int n_layers, const float* 
     const long long oidx = static_cast<long long>(b) * M.cout * ne + static_cast<long long>(o) * ne + e;
     M.w32[oidx] = wn;
     if (M.dw32) M.dw32[oidx] = dwn;
-    const __half wh = __float2half_rn(wn);
-    const __half wl = __float2half_rn(wn - __half2float(wh));
-    const __half dh = __float2half_rn(dwn);
+    // operands are packed scaled by kWeightScale (a power of two, undone exactly in the conv
+    // epilogue) so that lo = W - hi(W) ~ 2^-12 |W| stays a NORMAL fp16 number: unscaled, the lo
+    // part of a typical demodulated weight (~0.02) is subnormal and keeps only ~5 bits.
+    const float ws = wn * kWeightScale, dws_ = dwn * kWeightScale;
+    const __half wh = __float2half_rn(ws);
+    const __half wl = __float2half_rn(ws - __half2float(wh));
+    const __half dh = __float2half_rn(dws_);
     const int kc = M.kc16 ? 0 : (i >> 6);
     for (int r = 0; r < M.n_rules; ++r) {
       const EmitRule R = M.rules[r];
       const __half v = R.what == EMIT_WH ? wh : (R.what == EMIT_WL ? wl : dh);
       const long long tile = M.tap_tile[tap] + kc * M.kc_stride + R.kind * M.kind_stride;
       const int col = M.kc16 ? (R.kcol + i) : (i & 63);
-      M.dst[sample_off + (tile * M.nrs + R.row_base + o) * rowlen + col] = v;
+      const int row = R.row_base + ((M.k3 == 27 && tap / 9 == 1) ? R.alt_kd1 : 0) + o;
+      M.dst[sample_off + (tile * M.nrs + row) * rowlen + col] = v;
     }
   }
 }

@@ -27,6 +27,8 @@ constexpr int kMaxGroups = 64;
 constexpr int kMaxAMaps = 32;
 constexpr int kConvThreads = 256;
 constexpr int kSmemLimit = 227 * 1024;
+constexpr float kWeightScale = 256.0f;          // packed weights carry this factor (see modulate_kernel)
+constexpr float kInvWeightScale = 1.0f / 256.0f;
 
 struct MmaOp {
   uint8_t a;        // A operand block of the group (0/1)
@@ -74,7 +76,7 @@ struct alignas(128) ConvLaunch {
   int32_t cout;             // output channels (primal)
   int32_t vel;              // accumulator holds [y | dy]
   int32_t act;              // LeakyReLU
-  int32_t pad_;
+  int32_t acc3;             // accumulator columns are [y0 | dy | y1 | y2] (one primal accumulator per kd)
 };
 
 // Per-call arguments of the last layer's fused model tail.
@@ -363,13 +365,13 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
             for (int c = 0; c < 3; ++c) {
               const float x0 = scale_in_dtype(load_as_f32(fa.src, sidx + c * fa.src_sc, fa.src_dtype),
                                               fa.in_norm, fa.src_dtype);
-              float net = __uint_as_float(v[c]) + bias_s[c];
+              float net = __uint_as_float(v[c]) * kInvWeightScale + bias_s[c];
               if (fa.vel != nullptr) {
-                const float dnet = __uint_as_float(v[8 + c]);
+                const float dnet = __uint_as_float(v[8 + c]) * kInvWeightScale;
                 store_from_f32(fa.vel, oidx + c * fa.o_sc, fa.out_dtype,
                                round_to_dtype(dnet * fa.dx_norm + x0 * fa.x0_norm, fa.mid_dtype));
               } else {
-                net += __uint_as_float(v[8 + c]);     // displacement-only: columns 8..10 hold xh*Wl
+                net += __uint_as_float(v[8 + c]) * kInvWeightScale;     // displacement-only: columns 8..10 hold xh*Wl
               }
               store_from_f32(fa.disp, oidx + c * fa.o_sc, fa.out_dtype,
                              round_to_dtype((net + x0) * fa.six, fa.mid_dtype));
@@ -379,6 +381,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
           const int cout = L->cout;
           const bool vel = L->vel != 0;
           const bool act = L->act != 0;
+          const bool acc3 = L->acc3 != 0;
           const int pc = par & 1, pb2 = (par >> 1) & 1, pa2 = (par >> 2) & 1;
           const int64_t voff = static_cast<int64_t>(d0) * L->out_sd + static_cast<int64_t>(h) * L->out_sh +
                                static_cast<int64_t>(w) * L->out_sw + pc * L->par_ow + pb2 * L->par_oh +
@@ -393,13 +396,28 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
             tmem_ld_wait();
             tmem_st32_zero(taddr + c);
             if (vel) tmem_st32_zero(taddr + cout + c);
+            if (acc3) {
+              // per-kd primal accumulators: each saw a third of the truncating accumulations at
+              // ~1/sqrt(3) of the magnitude; combine them with round-to-nearest fp32 adds
+              uint32_t y1[32];
+              tmem_ld32(taddr + 2 * cout + c, y1);
+              tmem_ld_wait();
+              tmem_st32_zero(taddr + 2 * cout + c);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) y[i] = __float_as_uint(__uint_as_float(y[i]) + __uint_as_float(y1[i]));
+              tmem_ld32(taddr + 3 * cout + c, y1);
+              tmem_ld_wait();
+              tmem_st32_zero(taddr + 3 * cout + c);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) y[i] = __float_as_uint(__uint_as_float(y[i]) + __uint_as_float(y1[i]));
+            }
             uint32_t ph[16], pl[16], pd[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-              float y0 = __uint_as_float(y[i]) + bias_s[c + i];
-              float y1 = __uint_as_float(y[i + 1]) + bias_s[c + i + 1];
-              float d0v = vel ? __uint_as_float(dy[i]) : 0.f;
-              float d1v = vel ? __uint_as_float(dy[i + 1]) : 0.f;
+              float y0 = __uint_as_float(y[i]) * kInvWeightScale + bias_s[c + i];
+              float y1 = __uint_as_float(y[i + 1]) * kInvWeightScale + bias_s[c + i + 1];
+              float d0v = vel ? __uint_as_float(dy[i]) * kInvWeightScale : 0.f;
+              float d1v = vel ? __uint_as_float(dy[i + 1]) * kInvWeightScale : 0.f;
               if (act) {
                 d0v = y0 > 0.f ? d0v : 0.01f * d0v;
                 d1v = y1 > 0.f ? d1v : 0.01f * d1v;

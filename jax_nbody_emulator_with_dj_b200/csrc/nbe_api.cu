@@ -28,10 +28,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 enum ConvType { T_CONV3 = 0, T_SKIP1 = 1, T_DOWN = 2, T_UP = 3 };
-enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_COUNT };
+enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_COUNT };
 struct InstInfo { int nrs, dc, tm; bool fin; };
 const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32, 16, 2, true},
-                                 {128, 64, 2, false},  {64, 64, 2, false},   {256, 128, 1, false}};
+                                 {128, 64, 2, false},  {64, 64, 2, false},   {256, 128, 1, false},
+                                 {128, 256, 2, false}, {256, 512, 1, false}};
 
 // activation tensors of the net
 enum ActId {
@@ -176,8 +177,9 @@ int build_static(nbe_ctx* ctx) {
   const bool split = ctx->precision == NBE_PREC_SPLIT;
   ctx->sl.clear();
   auto L = [&](const char* b, const char* l) { return find_layer(ctx, b, l); };
-  auto inst64 = [&]() { return vel ? I_128_128_2 : (split ? I_128_64_2 : I_64_64_2); };
-  auto inst128 = [&]() { return vel ? I_256_256_1 : (split ? I_256_128_2 : I_128_128_2); };
+  // vel + split precision: one primal accumulator per kd ("acc3")
+  auto inst64 = [&]() { return vel ? (split ? I_128_256_2 : I_128_128_2) : (split ? I_128_64_2 : I_64_64_2); };
+  auto inst128 = [&]() { return vel ? (split ? I_256_512_1 : I_256_256_1) : (split ? I_256_128_2 : I_128_128_2); };
 
   auto add = [&](const std::string& name, int inst, int in_ref, int out_act, int cout,
                  std::vector<ConvPart> parts) {
@@ -256,11 +258,13 @@ int build_static(nbe_ctx* ctx) {
       (void)k3;
       // emit rules
       int nr = 0;
-      auto rule = [&](int what, int kind, int row, int kcol) {
+      auto rule = [&](int what, int kind, int row, int kcol, int alt = 0) {
         M.rules[nr].what = static_cast<int8_t>(what); M.rules[nr].kind = static_cast<int8_t>(kind);
         M.rules[nr].row_base = static_cast<int16_t>(row); M.rules[nr].kcol = static_cast<int16_t>(kcol);
+        M.rules[nr].alt_kd1 = static_cast<int16_t>(alt);
         ++nr;
       };
+      const bool acc3 = vel && split && !ii.fin;
       const int C = ly.cout;
       if (ii.fin) {
         if (vel) {
@@ -274,7 +278,9 @@ int build_static(nbe_ctx* ctx) {
         rule(EMIT_WH, 0, 0, 0); rule(EMIT_WH, 0, 0, 3); rule(EMIT_WL, 0, 0, 6);
         if (vel) rule(EMIT_DW, 0, C, 0);
       } else if (vel) {
-        rule(EMIT_WH, 0, 0, 0); rule(EMIT_DW, 0, C, 0);
+        // main stage [Wh | dW]; in acc3 mode the kd == 1 taps are packed [dW | Wh] so that one
+        // N = 2C MMA lands on the adjacent accumulator blocks (dy, y1)
+        rule(EMIT_WH, 0, 0, 0, acc3 ? C : 0); rule(EMIT_DW, 0, C, 0, acc3 ? -C : 0);
         if (split) { rule(EMIT_WL, 1, 0, 0); rule(EMIT_WH, 1, C, 0); }
       } else {
         rule(EMIT_WH, 0, 0, 0);
@@ -463,7 +469,8 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
         const int nk = k16 ? 1 : nkind;
         const int C = ly.cout;
         const int tb = k16 ? p.tile_base16 : p.tile_base64;
-        auto fill_ops = [&](GroupDesc& G, int kind, const Src& sc, int par) {
+        auto fill_ops = [&](GroupDesc& G, int kind, const Src& sc, int par, int kd) {
+          const bool acc3 = vel && split && !ii.fin && !k16;
           const __half* ph = hi(sc.act);
           if (k16) {
             G.n_a = 1; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par)); G.a_map[1] = -1;
@@ -495,7 +502,18 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           }
           if (vel) {
             G.n_a = 2; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par));
-            if (kind == 0) {         // [Wh | dW]:  D[0:2C] = xh*[Wh|dW];  D[C:2C] += dx*Wh
+            if (kind == 0 && acc3 && kd == 1) {   // [dW | Wh]:  D[C:3C] += xh*[dW|Wh] -> (dy, y1);  dy += dx*Wh
+              G.a_map[1] = static_cast<int16_t>(get_map(pd, sc.act, par));
+              G.n_ops = 2;
+              G.ops[0] = MmaOp{0, static_cast<uint8_t>(2 * C / 8), 0, static_cast<uint16_t>(C), 0};
+              G.ops[1] = MmaOp{1, static_cast<uint8_t>(C / 8), static_cast<uint16_t>(C), static_cast<uint16_t>(C), 0};
+            } else if (kind == 0 && acc3 && kd == 2) {   // [Wh | dW]:  y2 += xh*Wh;  dy += xh*dW + dx*Wh
+              G.a_map[1] = static_cast<int16_t>(get_map(pd, sc.act, par));
+              G.n_ops = 3;
+              G.ops[0] = MmaOp{0, static_cast<uint8_t>(C / 8), 0, static_cast<uint16_t>(3 * C), 0};
+              G.ops[1] = MmaOp{0, static_cast<uint8_t>(C / 8), static_cast<uint16_t>(C), static_cast<uint16_t>(C), 0};
+              G.ops[2] = MmaOp{1, static_cast<uint8_t>(C / 8), 0, static_cast<uint16_t>(C), 0};
+            } else if (kind == 0) {  // [Wh | dW]:  D[0:2C] = xh*[Wh|dW];  D[C:2C] += dx*Wh
               G.a_map[1] = static_cast<int16_t>(get_map(pd, sc.act, par));
               G.n_ops = 2;
               G.ops[0] = MmaOp{0, static_cast<uint8_t>(2 * C / 8), 0, 0, 0};
@@ -519,7 +537,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
             G.ops[0] = MmaOp{0, static_cast<uint8_t>(C / 8), 0, 0, 0};
           }
         };
-        auto mk = [&](const Src& sc, int par, int dw_, int dh_, int dd_, int ntaps, int tile0, int kind) {
+        auto mk = [&](const Src& sc, int par, int dw_, int dh_, int dd_, int ntaps, int tile0, int kind, int kd = -1) {
           GroupDesc G;
           memset(&G, 0, sizeof G);
           G.ntaps = static_cast<int8_t>(ntaps); G.kc16 = k16 ? 1 : 0; G.c0 = static_cast<int16_t>(sc.c0);
@@ -529,7 +547,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           G.pitch = static_cast<int8_t>(ntaps == 9 ? 10 : 8);
           cur_box_w = G.pitch;
           cur_kind = k16 ? 0 : kind;
-          fill_ops(G, kind, sc, par);
+          fill_ops(G, kind, sc, par, kd);
           if (G.a_map[0] < 0 || (G.n_a == 2 && G.a_map[1] < 0)) bad = true;
           push(G);
         };
@@ -540,8 +558,8 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           for (int kd = 0; kd < 3; ++kd)
             for (int q = 0; q < nkc; ++q) for (int kind = 0; kind < nk; ++kind) {
               const int t0 = tb + ((kd * nkc + q) * nk + kind) * 9;
-              if (wide) mk(p.src[q], -1, 0, 0, kd, 9, t0, kind);
-              else for (int kw = 0; kw < 3; ++kw) mk(p.src[q], -1, kw, 0, kd, 3, t0 + kw * 3, kind);
+              if (wide) mk(p.src[q], -1, 0, 0, kd, 9, t0, kind, kd);
+              else for (int kw = 0; kw < 3; ++kw) mk(p.src[q], -1, kw, 0, kd, 3, t0 + kw * 3, kind, kd);
             }
           H.flops += 2.0 * ly.cout * ly.cin * 27 * vout * m;
         } else if (p.type == T_SKIP1) {
@@ -565,6 +583,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
       if (bad) { delete P; return fail(ctx, NBE_ERR_STATE, "launch %s: too many groups / tensor maps", s.name.c_str()); }
       H.G.n_groups = ng;
       Lc.cout = s.cout; Lc.vel = vel ? 1 : 0; Lc.act = 1;
+      Lc.acc3 = (vel && split && !ii.fin) ? 1 : 0;
       Lc.bias = ctx->d_bias + s.bias_off;
       if (!ii.fin) {
         Lc.out_h_ptr = hi(s.out_act);
@@ -620,6 +639,8 @@ cudaError_t launch_conv(int inst, const ConvLaunch* dl, const GroupTable& gt, co
     case I_128_64_2: return launch_inst<128, 64, 2, false>(dl, gt, fa, grid, st);
     case I_64_64_2: return launch_inst<64, 64, 2, false>(dl, gt, fa, grid, st);
     case I_256_128_2: return launch_inst<256, 128, 1, false>(dl, gt, fa, grid, st);
+    case I_128_256_2: return launch_inst<128, 256, 2, false>(dl, gt, fa, grid, st);
+    case I_256_512_1: return launch_inst<256, 512, 1, false>(dl, gt, fa, grid, st);
   }
   return cudaErrorInvalidValue;
 }

@@ -106,13 +106,31 @@ def g_box64():
     return dict(disp=d.astype(np.float32), vel=v.astype(np.float32), z=z, Om=Om, seed=64, size=size, ndiv=ndiv)
 
 
+def g_n224():
+    """Production subbox size (BASELINE config 3): 224^3 -> 128^3.  fp64 convs do not fit in this
+    container's RAM at this size, so the truth is the fp32 oracle (5e-7 from fp64 at smaller
+    sizes); stored on a stride-4 subsample of the output (32^3 points per channel)."""
+    x = field((1, 3, 224, 224, 224), 224)
+    d, v = run(x, 0.5, 0.3, dtype=torch.float32)
+    h = torch.float16
+    r1 = lambda t: t.to(h).to(t.dtype)
+    def r2(t):
+        a = t.to(h).to(t.dtype); return a + (t - a).to(h).to(t.dtype)
+    Dz = float(np.float32(oc.growth_factor(0.5, 0.3))); vf = float(np.float32(oc.vel_norm(0.5, 0.3)))
+    net = Net(True, True, torch.float32, ops=dict(xp=r2, wp=r2, xt=r1, wt=r1, dw=r1, dx=r1))
+    de, ve = [t.numpy() for t in net.forward(P, x, float(np.float32(0.3)), Dz, vf)]
+    sub = (slice(None), slice(None), slice(None, None, 4), slice(None, None, 4), slice(None, None, 4))
+    return dict(disp=d[sub].astype(np.float32), vel=v[sub].astype(np.float32), emu_disp=rel(de, d), emu_vel=rel(ve, v),
+                z=0.5, Om=0.3, seed=224, N=224, stride=4, truth='fp32 oracle')
+
+
 def cand(kind, seed):
     if kind == 'noncubic':
         return with_cond(field((1, 3, 104, 112, 120), seed), 1.0, 0.25, seed=seed, shape=(104, 112, 120))
     return with_cond(field((1, 3, 128, 128, 128), seed), 0.5, 0.3, seed=seed, shape=(128, 128, 128))
 
 
-ALL = dict(illcond=g_illcond, box64=g_box64, n104=g_n104, batch2=g_batch2, noncubic=g_noncubic, box=g_box, n128=g_n128)
+ALL = dict(n224=g_n224, illcond=g_illcond, box64=g_box64, n104=g_n104, batch2=g_batch2, noncubic=g_noncubic, box=g_box, n128=g_n128)
 for name in (sys.argv[1:] or list(ALL)):
     t = time.time()
     r = cand(*name.split('_')[1:3][:1], int(name.split('_')[2])) if name.startswith('cand_') else ALL[name]()
