@@ -25,7 +25,7 @@ namespace nbe {
 
 constexpr int kMaxGroups = 64;
 constexpr int kMaxAMaps = 32;
-constexpr int kConvThreads = 256;
+constexpr int kConvThreads = 384;          // 4 pipeline warps + 8 epilogue warps
 constexpr int kSmemLimit = 227 * 1024;
 constexpr float kWeightScale = 256.0f;          // packed weights carry this factor (see modulate_kernel)
 constexpr float kInvWeightScale = 1.0f / 256.0f;
@@ -179,7 +179,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::kNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < Cfg::kNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -194,7 +194,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
   // Accumulators start at zero and are re-zeroed by the epilogue after each read, so every MMA
   // accumulates and the launch may order its terms freely (small lo-products first: the tensor
   // core truncates on accumulation, and truncation error scales with the running sum).
-  if (warp >= 4) {
+  if (warp >= 4 && warp < 8) {
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     if constexpr (DC >= 32) {
       for (int c = 0; c < Cfg::kNBuf * TM * DC; c += 32) tmem_st32_zero(lane_base + c);
@@ -337,9 +337,12 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
       if (++buf == Cfg::kNBuf) { buf = 0; pacc ^= 1; }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------ epilogue (128 threads, thread <-> row)
+    // ------------------------------------------------ epilogue (2 x 128 threads, thread <-> row)
+    // two warp sets share the work of an item: with TM == 2 each set owns one tile, with
+    // TM == 1 they take alternate 32-channel chunks
     const int q = warp & 3;                       // TMEM lane quarter of this warp
     const int r = q * 32 + lane;                  // accumulator row
+    const int eg = (warp - 4) >> 2;               // epilogue warp set 0 / 1
     uint32_t buf = 0, pacc = 0;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       int par, w0, h0, d0;
@@ -348,11 +351,13 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
       tc_fence_after();
 #pragma unroll
       for (int t = 0; t < TM; ++t) {
+        if (TM == 2 && t != eg) continue;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (buf * TM + t) * DC;
         const int w = w0 + (r & 7);
         const int h = h0 + t * 16 + (r >> 3);
         const bool valid = (w < out_w) && (h < out_h);
         if constexpr (FINAL) {
+          if (TM == 1 && eg != 0) continue;
           uint32_t v[16];
           tmem_ld16(taddr, v);
           tmem_ld_wait();
@@ -389,7 +394,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
           __half* oh = L->out_h_ptr + voff;
           __half* ol = L->out_l_ptr ? L->out_l_ptr + voff : nullptr;
           __half* od = L->out_d_ptr ? L->out_d_ptr + voff : nullptr;
-          for (int c = 0; c < cout; c += 32) {
+          for (int c = (TM == 1 ? eg * 32 : 0); c < cout; c += (TM == 1 ? 64 : 32)) {
             uint32_t y[32], dy[32];
             tmem_ld32(taddr + c, y);
             if (vel) tmem_ld32(taddr + cout + c, dy);
@@ -434,10 +439,14 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
             }
             if (valid) {
 #pragma unroll
-              for (int v4 = 0; v4 < 4; ++v4) {
-                st_global_v4(oh + c + v4 * 8, make_uint4(ph[4 * v4], ph[4 * v4 + 1], ph[4 * v4 + 2], ph[4 * v4 + 3]));
-                if (ol) st_global_v4(ol + c + v4 * 8, make_uint4(pl[4 * v4], pl[4 * v4 + 1], pl[4 * v4 + 2], pl[4 * v4 + 3]));
-                if (od) st_global_v4(od + c + v4 * 8, make_uint4(pd[4 * v4], pd[4 * v4 + 1], pd[4 * v4 + 2], pd[4 * v4 + 3]));
+              for (int v8 = 0; v8 < 2; ++v8) {
+                const int j = 8 * v8;
+                st_global_v8(oh + c + v8 * 16, make_uint4(ph[j], ph[j + 1], ph[j + 2], ph[j + 3]),
+                             make_uint4(ph[j + 4], ph[j + 5], ph[j + 6], ph[j + 7]));
+                if (ol) st_global_v8(ol + c + v8 * 16, make_uint4(pl[j], pl[j + 1], pl[j + 2], pl[j + 3]),
+                                     make_uint4(pl[j + 4], pl[j + 5], pl[j + 6], pl[j + 7]));
+                if (od) st_global_v8(od + c + v8 * 16, make_uint4(pd[j], pd[j + 1], pd[j + 2], pd[j + 3]),
+                                     make_uint4(pd[j + 4], pd[j + 5], pd[j + 6], pd[j + 7]));
               }
             }
           }

@@ -222,4 +222,11 @@ __device__ __forceinline__ void st_global_v4(void* p, uint4 v) {
                : "memory");
 }
 
+// 256-bit store (sm_100): one full 32-byte sector per lane
+__device__ __forceinline__ void st_global_v8(void* p, uint4 a, uint4 b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z),
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 }  // namespace nbe
