@@ -761,6 +761,9 @@ int check_box_args(nbe_ctx* ctx, const void* in, const int32_t* size, const int3
   if (in_dtype < 0 || in_dtype > 2 || out_dtype < 0 || out_dtype > 2) return fail(ctx, NBE_ERR_ARG, "bad dtype");
   for (int d = 0; d < 3; ++d)
     if (plen[d] - crop[d] != 96) return fail(ctx, NBE_ERR_ARG, "padding must be 48 per side (the models hard-code the 48-voxel crop)");
+  // validate the padded subbox shape before any copy is enqueued
+  int tmp[A_COUNT];
+  for (int d = 0; d < 3; ++d) { int rc = chain(ctx, plen[d], tmp); if (rc) return rc; }
   return NBE_OK;
 }
 
@@ -1067,7 +1070,7 @@ int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32
                           const bool run_ends = last || (ai + 3)[0] != ai[0] || (s - run_start + 1) == run_full;
                           return run_ends ? flush_run(s) : NBE_OK;
                         });
-  cudaError_t e1 = cudaStreamSynchronize(st);
+  cudaError_t e1 = cudaStreamSynchronize(st);      // also on error paths: the caller's buffers must be quiescent
   cudaError_t e2 = cudaStreamSynchronize(cs);
   cudaEventDestroy(done);
   if (rc) return rc;

@@ -127,15 +127,15 @@ class SubboxProcessor:
         single asynchronous DMA; cached for repeated calls on the same buffer."""
         torch = _torch()
         key = (box.ctypes.data, box.nbytes)
-        if self._pinned_in == key:
+        if self._pinned_in is not None and self._pinned_in[0] == key:
             return
         rt = torch.cuda.cudart()
         if self._pinned_in is not None:
-            rt.cudaHostUnregister(self._pinned_in[0])
+            rt.cudaHostUnregister(self._pinned_in[0][0])
             self._pinned_in = None
         try:
             if int(rt.cudaHostRegister(box.ctypes.data, box.nbytes, 0)) == 0:
-                self._pinned_in = key
+                self._pinned_in = (key, box)     # keep the array alive while it is page-locked
         except Exception:
             pass                     # already pinned (e.g. a torch pin_memory tensor) or not registrable
 
