@@ -115,6 +115,11 @@ int nbe_process_box_dev(nbe_ctx* ctx, const void* box_dev, int in_dtype, const i
                         const int32_t* add_idx0, int sub_first, int sub_count, float Dz, float vel_fac,
                         void* disp_dev, void* vel_dev, int out_dtype, void* stream);
 
+/* Page-lock (cudaHostRegister) / unlock a caller-owned host buffer used with nbe_process_box.
+ * nbe_host_register returns 1 if it registered the buffer, 0 if it already was page-locked.  */
+int nbe_host_register(nbe_ctx* ctx, void* ptr, size_t bytes);
+int nbe_host_unregister(nbe_ctx* ctx, void* ptr);
+
 /* Bytes of device memory the context needs for one (n0,n1,n2) sample (activation arena). */
 size_t nbe_workspace_bytes(nbe_ctx* ctx, const int32_t dims[3]);
 

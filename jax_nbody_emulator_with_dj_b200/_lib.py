@@ -22,7 +22,7 @@ NBE_PREC_SPLIT, NBE_PREC_FP16 = 0, 1
 EXPORTS = (
     "nbe_create", "nbe_destroy", "nbe_last_error", "nbe_version", "nbe_set_params", "nbe_set_precision",
     "nbe_modulate", "nbe_get_modulated", "nbe_forward", "nbe_process_box", "nbe_process_box_dev",
-    "nbe_workspace_bytes",
+    "nbe_workspace_bytes", "nbe_host_register", "nbe_host_unregister",
     "nbe_launch_count", "nbe_set_profiling", "nbe_get_profile", "nbe_selftest", "nbe_debug_read_act",
 )
 
@@ -86,6 +86,8 @@ def load():
                                         C.c_float, C.c_float, vp, vp, C.c_int]
         lib.nbe_process_box_dev.argtypes = [vp, vp, C.c_int, i32p, i32p, i32p, i32p, i32p, C.c_int, C.c_int,
                                             C.c_float, C.c_float, vp, vp, C.c_int, vp]
+        lib.nbe_host_register.argtypes = [vp, vp, C.c_size_t]
+        lib.nbe_host_unregister.argtypes = [vp, vp]
         lib.nbe_workspace_bytes.argtypes = [vp, i32p]
         lib.nbe_workspace_bytes.restype = C.c_size_t
         lib.nbe_launch_count.argtypes = [vp, C.c_int]

@@ -1079,6 +1079,30 @@ int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32
   return NBE_OK;
 }
 
+// Page-lock / unlock a caller-owned host buffer so that nbe_process_box's copies are single
+// asynchronous DMAs.  Returns 1 if this call registered the buffer, 0 if it was already
+// page-locked (nothing to undo), negative on error.  Never leaves a sticky CUDA error behind.
+int nbe_host_register(nbe_ctx* ctx, void* ptr, size_t bytes) {
+  if (!ctx || !ptr) return NBE_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeHost) return 0;
+  cudaGetLastError();
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+  if (e == cudaSuccess) return 1;
+  cudaGetLastError();
+  if (e == cudaErrorHostMemoryAlreadyRegistered) return 0;
+  return fail(ctx, NBE_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e));
+}
+
+int nbe_host_unregister(nbe_ctx* ctx, void* ptr) {
+  if (!ctx || !ptr) return NBE_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaHostUnregister(ptr);
+  cudaGetLastError();
+  return e == cudaSuccess ? NBE_OK : NBE_ERR_CUDA;
+}
+
 int64_t nbe_launch_count(nbe_ctx* ctx, int reset) {
   if (!ctx) return -1;
   const int64_t n = ctx->launches;

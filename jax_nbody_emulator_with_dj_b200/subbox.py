@@ -122,22 +122,20 @@ class SubboxProcessor:
             self._out_range = None
         return self._out[1][1], self._out[2][1]
 
-    def _pin_input(self, box):
-        """Page-lock the caller's array in place (cudaHostRegister) so that the upload is a
-        single asynchronous DMA; cached for repeated calls on the same buffer."""
-        torch = _torch()
+    def _pin_input(self, eng, box):
+        """Page-lock the caller's array in place so that the upload is a single asynchronous DMA;
+        cached for repeated calls on the same buffer (which is kept alive while registered)."""
+        import ctypes as C
         key = (box.ctypes.data, box.nbytes)
         if self._pinned_in is not None and self._pinned_in[0] == key:
             return
-        rt = torch.cuda.cudart()
         if self._pinned_in is not None:
-            rt.cudaHostUnregister(self._pinned_in[0][0])
+            if self._pinned_in[2]:
+                eng.lib.nbe_host_unregister(eng.h, C.c_void_p(self._pinned_in[0][0]))
             self._pinned_in = None
-        try:
-            if int(rt.cudaHostRegister(box.ctypes.data, box.nbytes, 0)) == 0:
-                self._pinned_in = (key, box)     # keep the array alive while it is page-locked
-        except Exception:
-            pass                     # already pinned (e.g. a torch pin_memory tensor) or not registrable
+        rc = eng.lib.nbe_host_register(eng.h, C.c_void_p(box.ctypes.data), box.nbytes)
+        if rc >= 0:
+            self._pinned_in = (key, box, rc == 1)
 
     def process_box(self, input_box, z, Om, desc="Processing subboxes", show_progress=True,
                     shard=None, gather="all", copy=True):
@@ -188,7 +186,7 @@ class SubboxProcessor:
             if vel is not None:
                 vel.fill(0)
         self._out_range = (lo, hi)
-        self._pin_input(box)
+        self._pin_input(eng, box)
         bar = None
         if show_progress:
             from tqdm import tqdm
