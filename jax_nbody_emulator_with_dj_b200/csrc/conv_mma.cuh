@@ -31,11 +31,11 @@ constexpr float kWeightScale = 256.0f;          // packed weights carry this fac
 constexpr float kInvWeightScale = 1.0f / 256.0f;
 
 struct MmaOp {
-  uint8_t a;        // A operand block of the group (0/1)
-  uint8_t n8;       // N / 8
-  uint16_t b_row;   // first row of the B stage (multiple of 8)
+  uint16_t a_off;   // byte offset >> 4 of the A operand block inside the activation stage
+  uint16_t b_off;   // byte offset >> 4 of the first B row inside the weight stage
   uint16_t d_col;   // first accumulator column
-  uint16_t pad_;
+  uint8_t n8;       // N / 8
+  uint8_t pad_;
 };
 
 struct GroupDesc {
@@ -168,6 +168,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int kIssuers = TM == 2 ? 2 : 1;
 
   const int n_groups = gt.n_groups;
   const int out_w = L->out_w, out_h = L->out_h, out_d = L->out_d;
@@ -177,9 +178,11 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
   const long long n_items = 1ll * n_par * out_d * tiles_h * tiles_w;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < Cfg::kNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < Cfg::kNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); }
+    // kIssuers MMA-issuing warps (one per M-tile when TM == 2): each commits to the empty / full
+    // barriers, so those expect kIssuers arrivals
+    for (int i = 0; i < Cfg::kNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], kIssuers); }
+    for (int i = 0; i < Cfg::kNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], kIssuers); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], kIssuers); mbar_init(&acc_empty[i], 256); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -256,10 +259,13 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
         }
       }
     }
-  } else if (warp == 2) {
-    // ------------------------------------------------ MMA issuer
+  } else if (warp == 2 || (warp == 3 && kIssuers == 2)) {
+    // ------------------------------------------------ MMA issuer(s)
     // The whole warp runs this loop with warp-uniform control flow and values (so they stay in
-    // uniform registers); lane 0 alone issues tcgen05.mma / tcgen05.commit.
+    // uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit.  With TM == 2 two
+    // warps issue, one per M-tile: the issue path (not the tensor pipe) was the limiter, and
+    // tile-disjoint accumulators keep the result independent of the interleaving.
+    const int my_tile = warp - 2;
     constexpr uint32_t idesc_base = umma_idesc_f16(128, 0, false);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0, buf = 0, pacc = 0;
@@ -281,8 +287,8 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
         uint32_t op_a[3], op_b[3], op_d[3], op_i[3];
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
-          op_a[o] = (static_cast<uint32_t>(G.ops[o].a) * Cfg::kABlk) >> 4;
-          op_b[o] = (static_cast<uint32_t>(G.ops[o].b_row) * rowb) >> 4;
+          op_a[o] = G.ops[o].a_off;
+          op_b[o] = G.ops[o].b_off;
           op_d[o] = G.ops[o].d_col;
           op_i[o] = idesc_base | (static_cast<uint32_t>(G.ops[o].n8) << 17);
         }
@@ -296,6 +302,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
           if (elect_one()) {
 #pragma unroll
             for (int t = 0; t < TM; ++t) {
+              if (kIssuers == 2 && t != my_tile) continue;
               const uint32_t d_tile = tmem_u + (buf * TM + t) * DC;
               const uint32_t kw = ntaps == 9 ? static_cast<uint32_t>(j) / 3u : 0u;
               const uint32_t kh = ntaps == 9 ? static_cast<uint32_t>(j) % 3u : static_cast<uint32_t>(j);

@@ -469,13 +469,24 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
         const int nk = k16 ? 1 : nkind;
         const int C = ly.cout;
         const int tb = k16 ? p.tile_base16 : p.tile_base64;
+        // OP(a, n8, b_row, d_col) -> device layout with byte offsets >> 4 precomputed
+        const int a_blk16 = ((16 * ii.tm + 2) * 10 * 128 + 1023) / 1024 * 1024 / 16;
+        auto OP = [&](int a, int n8, int b_row, int d_col) {
+          MmaOp o;
+          o.a_off = static_cast<uint16_t>(a * a_blk16);
+          o.b_off = static_cast<uint16_t>(b_row * (k16 ? 32 : 128) / 16);
+          o.d_col = static_cast<uint16_t>(d_col);
+          o.n8 = static_cast<uint8_t>(n8);
+          o.pad_ = 0;
+          return o;
+        };
         auto fill_ops = [&](GroupDesc& G, int kind, const Src& sc, int par, int kd) {
           const bool acc3 = vel && split && !ii.fin && !k16;
           const __half* ph = hi(sc.act);
           if (k16) {
             G.n_a = 1; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par)); G.a_map[1] = -1;
             G.n_ops = 1;
-            G.ops[0] = MmaOp{0, static_cast<uint8_t>((vel ? 2 * C : C) / 8), 0, 0, 0};
+            G.ops[0] = OP(0, (vel ? 2 * C : C) / 8, 0, 0);
             return;
           }
           const __half* pl = split ? lo(sc.act) : nullptr;
@@ -485,18 +496,18 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
               G.n_a = 2; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par));
               G.a_map[1] = static_cast<int16_t>(get_map(kind == 0 ? pd : pl, sc.act, par));
               G.n_ops = 2;
-              G.ops[0] = MmaOp{0, 2, 0, 0, 0};
-              G.ops[1] = MmaOp{1, 2, 16, 0, 0};
+              G.ops[0] = OP(0, 2, 0, 0);
+              G.ops[1] = OP(1, 2, 16, 0);
             } else if (split) {
               G.n_a = 2; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par));
               G.a_map[1] = static_cast<int16_t>(get_map(pl, sc.act, par));
               G.n_ops = 2;
-              G.ops[0] = MmaOp{0, 2, 0, 0, 0};
-              G.ops[1] = MmaOp{1, 2, 16, 0, 0};
+              G.ops[0] = OP(0, 2, 0, 0);
+              G.ops[1] = OP(1, 2, 16, 0);
             } else {
               G.n_a = 1; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par)); G.a_map[1] = -1;
               G.n_ops = 1;
-              G.ops[0] = MmaOp{0, 2, 0, 0, 0};
+              G.ops[0] = OP(0, 2, 0, 0);
             }
             return;
           }
@@ -505,36 +516,36 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
             if (kind == 0 && acc3 && kd == 1) {   // [dW | Wh]:  D[C:3C] += xh*[dW|Wh] -> (dy, y1);  dy += dx*Wh
               G.a_map[1] = static_cast<int16_t>(get_map(pd, sc.act, par));
               G.n_ops = 2;
-              G.ops[0] = MmaOp{0, static_cast<uint8_t>(2 * C / 8), 0, static_cast<uint16_t>(C), 0};
-              G.ops[1] = MmaOp{1, static_cast<uint8_t>(C / 8), static_cast<uint16_t>(C), static_cast<uint16_t>(C), 0};
+              G.ops[0] = OP(0, 2 * C / 8, 0, C);
+              G.ops[1] = OP(1, C / 8, C, C);
             } else if (kind == 0 && acc3 && kd == 2) {   // [Wh | dW]:  y2 += xh*Wh;  dy += xh*dW + dx*Wh
               G.a_map[1] = static_cast<int16_t>(get_map(pd, sc.act, par));
               G.n_ops = 3;
-              G.ops[0] = MmaOp{0, static_cast<uint8_t>(C / 8), 0, static_cast<uint16_t>(3 * C), 0};
-              G.ops[1] = MmaOp{0, static_cast<uint8_t>(C / 8), static_cast<uint16_t>(C), static_cast<uint16_t>(C), 0};
-              G.ops[2] = MmaOp{1, static_cast<uint8_t>(C / 8), 0, static_cast<uint16_t>(C), 0};
+              G.ops[0] = OP(0, C / 8, 0, 3 * C);
+              G.ops[1] = OP(0, C / 8, C, C);
+              G.ops[2] = OP(1, C / 8, 0, C);
             } else if (kind == 0) {  // [Wh | dW]:  D[0:2C] = xh*[Wh|dW];  D[C:2C] += dx*Wh
               G.a_map[1] = static_cast<int16_t>(get_map(pd, sc.act, par));
               G.n_ops = 2;
-              G.ops[0] = MmaOp{0, static_cast<uint8_t>(2 * C / 8), 0, 0, 0};
-              G.ops[1] = MmaOp{1, static_cast<uint8_t>(C / 8), 0, static_cast<uint16_t>(C), 0};
+              G.ops[0] = OP(0, 2 * C / 8, 0, 0);
+              G.ops[1] = OP(1, C / 8, 0, C);
             } else {                 // [Wl | Wh]:  D[0:C] += xh*Wl + xl*Wh
               G.a_map[1] = static_cast<int16_t>(get_map(pl, sc.act, par));
               G.n_ops = 2;
-              G.ops[0] = MmaOp{0, static_cast<uint8_t>(C / 8), 0, 0, 0};
-              G.ops[1] = MmaOp{1, static_cast<uint8_t>(C / 8), static_cast<uint16_t>(C), 0, 0};
+              G.ops[0] = OP(0, C / 8, 0, 0);
+              G.ops[1] = OP(1, C / 8, C, 0);
             }
           } else if (split) {        // [Wh | Wl]:  D = xh*Wh + xh*Wl + xl*Wh
             G.n_a = 2; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par));
             G.a_map[1] = static_cast<int16_t>(get_map(pl, sc.act, par));
             G.n_ops = 3;
-            G.ops[0] = MmaOp{0, static_cast<uint8_t>(C / 8), 0, 0, 0};
-            G.ops[1] = MmaOp{0, static_cast<uint8_t>(C / 8), static_cast<uint16_t>(C), 0, 0};
-            G.ops[2] = MmaOp{1, static_cast<uint8_t>(C / 8), 0, 0, 0};
+            G.ops[0] = OP(0, C / 8, 0, 0);
+            G.ops[1] = OP(0, C / 8, C, 0);
+            G.ops[2] = OP(1, C / 8, 0, 0);
           } else {
             G.n_a = 1; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par)); G.a_map[1] = -1;
             G.n_ops = 1;
-            G.ops[0] = MmaOp{0, static_cast<uint8_t>(C / 8), 0, 0, 0};
+            G.ops[0] = OP(0, C / 8, 0, 0);
           }
         };
         auto mk = [&](const Src& sc, int par, int dw_, int dh_, int dd_, int ntaps, int tile0, int kind, int kd = -1) {
