@@ -1033,7 +1033,29 @@ int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32
   if ((rc = ensure(ctx, &ctx->d_box, &ctx->box_cap, in_bytes))) return rc;
   if ((rc = ensure(ctx, &ctx->d_disp, &ctx->out_cap, out_bytes))) return rc;
   if (ctx->vel && (rc = ensure(ctx, &ctx->d_velo, &ctx->velo_cap, out_bytes))) return rc;
-  CK(cudaMemcpyAsync(ctx->d_box, in_host, in_bytes, cudaMemcpyHostToDevice, st));
+  // Upload only the D-planes this range of subboxes reads (its slabs plus the 48-voxel halo,
+  // periodic): on 8 ranks that is ~30 % of the box instead of all of it.
+  {
+    const int per_ = plen[0] + plen[1] + plen[2];
+    std::vector<char> need(static_cast<size_t>(S0), 0);
+    for (int s = 0; s < sub_count; ++s) {
+      const int32_t* di = crop_idx + static_cast<size_t>(sub_first + s) * per_;
+      for (int i = 0; i < plen[0]; ++i) need[di[i]] = 1;
+    }
+    const size_t ies = dtype_size(in_dtype);
+    const size_t plane = static_cast<size_t>(S1) * S2 * ies;
+    for (int64_t d0 = 0; d0 < S0;) {
+      if (!need[d0]) { ++d0; continue; }
+      int64_t d1 = d0;
+      while (d1 < S0 && need[d1]) ++d1;
+      for (int c = 0; c < 3; ++c) {
+        const size_t off = (static_cast<size_t>(c) * S0 + d0) * plane;
+        CK(cudaMemcpyAsync(static_cast<uint8_t*>(ctx->d_box) + off, static_cast<const uint8_t*>(in_host) + off,
+                           static_cast<size_t>(d1 - d0) * plane, cudaMemcpyHostToDevice, st));
+      }
+      d0 = d1;
+    }
+  }
   const size_t es = dtype_size(out_dtype);
   cudaEvent_t done;
   CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
