@@ -113,6 +113,21 @@ class SubboxProcessor:
         self._out_range = None
         self._pinned_in = None     # (ptr, nbytes) of the host input currently page-locked
 
+    def close(self):
+        """Release the page-lock on the cached input buffer (also called on garbage collection: a
+        host array must never be freed while it is still registered with CUDA)."""
+        pin, self._pinned_in = getattr(self, "_pinned_in", None), None
+        if pin is not None and pin[2]:
+            try:
+                import ctypes as C
+                eng = Engine.get()
+                eng.lib.nbe_host_unregister(eng.h, C.c_void_p(pin[0][0]))
+            except Exception:
+                pass
+
+    def __del__(self):
+        self.close()
+
     def _outputs(self, shape, out_np):
         key = (shape, np.dtype(out_np).name, self.compute_vel)
         if self._out is None or self._out[0] != key:
