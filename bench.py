@@ -311,7 +311,10 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         t_e2e = float(dt.item()) / n_e2e
         own = (hi - lo) * int(np.prod(cfg.crop_size))
-        e2e = {"value": particles_total / t_e2e, "unit": "particles/s", "h2d_bytes_per_step": int(host.nbytes),
+        per = sum(plen)
+        tabs = crop_idx.reshape(n_sub, per)[lo:hi, :plen[0]]
+        planes = int(np.unique(tabs).size)          # D-planes this rank uploads (slab + halo)
+        e2e = {"value": particles_total / t_e2e, "unit": "particles/s", "h2d_bytes_per_step": int(3 * planes * S * S * 4),
                "d2h_bytes_per_step": int(2 * 3 * own * 4), "ms_per_step": t_e2e * 1e3,
                "api": "SubboxProcessor.process_box(host numpy) -> nbe_process_box"}
 

@@ -727,11 +727,12 @@ size_t dtype_size(int dt) { return dt == NBE_F32 ? 4 : 2; }
 // asynchronous on `stream`.  After subbox s has been enqueued `after(s)` is called (used by the
 // host wrapper to overlap the copy-back).
 template <class After>
-int process_box_core(nbe_ctx* ctx, const void* box_dev, int in_dtype, const int32_t size[3], const int32_t crop[3],
-                     const int32_t plen[3], const int32_t* crop_idx, const int32_t* add_idx0, int sub_first,
+int process_box_core(nbe_ctx* ctx, const void* box_dev, int in_dtype, const int32_t size[3], const int32_t size_out[3],
+                     const int32_t crop[3], const int32_t plen[3], const int32_t* crop_idx, const int32_t* add_idx0, int sub_first,
                      int sub_count, float Dz, float vel_fac, void* disp_dev, void* vel_dev, int out_dtype,
                      cudaStream_t st, After after) {
   const int64_t S0 = size[0], S1 = size[1], S2 = size[2];
+  const int64_t O0 = size_out[0], O1 = size_out[1], O2 = size_out[2];
   int rc;
   const int per = plen[0] + plen[1] + plen[2];
   const size_t idx_bytes = static_cast<size_t>(sub_count) * per * sizeof(int32_t);
@@ -750,10 +751,10 @@ int process_box_core(nbe_ctx* ctx, const void* box_dev, int in_dtype, const int3
     FinalArgs fa{};
     fa.src = box_dev; fa.src_dtype = in_dtype; fa.src_sc = pk.src_sc; fa.src_sd = pk.src_sd; fa.src_sh = pk.src_sh;
     fa.idx_d = pk.idx_d + 48; fa.idx_h = pk.idx_h + 48; fa.idx_w = pk.idx_w + 48;
-    const size_t base = (static_cast<size_t>(ai[0]) * S1 + ai[1]) * S2 + ai[2];
+    const size_t base = (static_cast<size_t>(ai[0]) * O1 + ai[1]) * O2 + ai[2];
     fa.disp = static_cast<uint8_t*>(disp_dev) + base * es;
     fa.vel = ctx->vel ? static_cast<uint8_t*>(vel_dev) + base * es : nullptr;
-    fa.out_dtype = out_dtype; fa.mid_dtype = in_dtype; fa.o_sc = S0 * S1 * S2; fa.o_sd = S1 * S2; fa.o_sh = S2;
+    fa.out_dtype = out_dtype; fa.mid_dtype = in_dtype; fa.o_sc = O0 * O1 * O2; fa.o_sd = O1 * O2; fa.o_sh = O2;
     fa.in_norm = pk.in_norm; fa.six = 6.0f; fa.dx_norm = vel_fac * 6.0f; fa.x0_norm = vel_fac * 6.0f / Dz;
     if ((rc = run_sample(ctx, P, 0, pk, fa, st))) return rc;
     if ((rc = after(s))) return rc;
@@ -1013,7 +1014,7 @@ int nbe_process_box_dev(nbe_ctx* ctx, const void* box_dev, int in_dtype, const i
   int rc = check_box_args(ctx, box_dev, size, crop, plen, crop_idx, add_idx0, disp_dev, vel_dev, sub_count, in_dtype, out_dtype);
   if (rc) return rc;
   CK(cudaSetDevice(ctx->device));
-  return process_box_core(ctx, box_dev, in_dtype, size, crop, plen, crop_idx, add_idx0, sub_first, sub_count, Dz,
+  return process_box_core(ctx, box_dev, in_dtype, size, size, crop, plen, crop_idx, add_idx0, sub_first, sub_count, Dz,
                           vel_fac, disp_dev, vel_dev, out_dtype, static_cast<cudaStream_t>(stream),
                           [](int) { return NBE_OK; });
 }
@@ -1028,35 +1029,50 @@ int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->own_stream, cs = ctx->copy_stream;
   const int64_t S0 = size[0], S1 = size[1], S2 = size[2];
-  const size_t in_bytes = static_cast<size_t>(3) * S0 * S1 * S2 * dtype_size(in_dtype);
-  const size_t out_bytes = static_cast<size_t>(3) * S0 * S1 * S2 * dtype_size(out_dtype);
+  const int per = plen[0] + plen[1] + plen[2];
+  const size_t ies = dtype_size(in_dtype), es = dtype_size(out_dtype);
+  const size_t plane_in = static_cast<size_t>(S1) * S2 * ies, plane_out = static_cast<size_t>(S1) * S2 * es;
+
+  // ---- device slabs hold only what this range of subboxes touches.
+  // input: the D-planes it reads (owned slabs + 48-voxel halo, periodic) compacted into slots in
+  // increasing plane order; the D gather tables are remapped plane -> slot.  On 8 ranks that is
+  // ~30 % of the box (upload and memory); it is also what lets a box larger than one GPU's HBM
+  // be processed when sharded (BASELINE config 5).
+  std::vector<int32_t> slot(static_cast<size_t>(S0), -1);
+  std::vector<int32_t> tabs(crop_idx + static_cast<size_t>(sub_first) * per,
+                            crop_idx + static_cast<size_t>(sub_first + sub_count) * per);
+  for (int s = 0; s < sub_count; ++s)
+    for (int i = 0; i < plen[0]; ++i) slot[tabs[static_cast<size_t>(s) * per + i]] = 0;
+  int64_t n_slots = 0;
+  for (int64_t d = 0; d < S0; ++d) if (slot[d] == 0) slot[d] = static_cast<int32_t>(n_slots++);
+  for (int s = 0; s < sub_count; ++s)
+    for (int i = 0; i < plen[0]; ++i) { int32_t& v = tabs[static_cast<size_t>(s) * per + i]; v = slot[v]; }
+  // output: the D-range [dlo, dhi) spanned by the owned blocks
+  int64_t dlo = S0, dhi = 0;
+  for (int s = 0; s < sub_count; ++s) {
+    const int32_t a0 = add_idx0[static_cast<size_t>(sub_first + s) * 3];
+    dlo = std::min<int64_t>(dlo, a0); dhi = std::max<int64_t>(dhi, a0 + crop[0]);
+  }
+  const int64_t ND = dhi - dlo;
+  // anchors relative to the output slab
+  std::vector<int32_t> anchors(add_idx0 + static_cast<size_t>(sub_first) * 3, add_idx0 + static_cast<size_t>(sub_first + sub_count) * 3);
+  for (int s = 0; s < sub_count; ++s) anchors[static_cast<size_t>(s) * 3] -= static_cast<int32_t>(dlo);
+
+  const size_t in_bytes = static_cast<size_t>(3) * n_slots * plane_in;
+  const size_t out_bytes = static_cast<size_t>(3) * ND * plane_out;
   if ((rc = ensure(ctx, &ctx->d_box, &ctx->box_cap, in_bytes))) return rc;
   if ((rc = ensure(ctx, &ctx->d_disp, &ctx->out_cap, out_bytes))) return rc;
   if (ctx->vel && (rc = ensure(ctx, &ctx->d_velo, &ctx->velo_cap, out_bytes))) return rc;
-  // Upload only the D-planes this range of subboxes reads (its slabs plus the 48-voxel halo,
-  // periodic): on 8 ranks that is ~30 % of the box instead of all of it.
-  {
-    const int per_ = plen[0] + plen[1] + plen[2];
-    std::vector<char> need(static_cast<size_t>(S0), 0);
-    for (int s = 0; s < sub_count; ++s) {
-      const int32_t* di = crop_idx + static_cast<size_t>(sub_first + s) * per_;
-      for (int i = 0; i < plen[0]; ++i) need[di[i]] = 1;
-    }
-    const size_t ies = dtype_size(in_dtype);
-    const size_t plane = static_cast<size_t>(S1) * S2 * ies;
-    for (int64_t d0 = 0; d0 < S0;) {
-      if (!need[d0]) { ++d0; continue; }
-      int64_t d1 = d0;
-      while (d1 < S0 && need[d1]) ++d1;
-      for (int c = 0; c < 3; ++c) {
-        const size_t off = (static_cast<size_t>(c) * S0 + d0) * plane;
-        CK(cudaMemcpyAsync(static_cast<uint8_t*>(ctx->d_box) + off, static_cast<const uint8_t*>(in_host) + off,
-                           static_cast<size_t>(d1 - d0) * plane, cudaMemcpyHostToDevice, st));
-      }
-      d0 = d1;
-    }
+  for (int64_t d0 = 0; d0 < S0;) {                        // runs of consecutive planes = consecutive slots
+    if (slot[d0] < 0) { ++d0; continue; }
+    int64_t d1 = d0;
+    while (d1 < S0 && slot[d1] >= 0) ++d1;
+    for (int c = 0; c < 3; ++c)
+      CK(cudaMemcpyAsync(static_cast<uint8_t*>(ctx->d_box) + (static_cast<size_t>(c) * n_slots + slot[d0]) * plane_in,
+                         static_cast<const uint8_t*>(in_host) + (static_cast<size_t>(c) * S0 + d0) * plane_in,
+                         static_cast<size_t>(d1 - d0) * plane_in, cudaMemcpyHostToDevice, st));
+    d0 = d1;
   }
-  const size_t es = dtype_size(out_dtype);
   cudaEvent_t done;
   CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
   // Copy-back policy: consecutive subboxes sharing a D anchor form a run; when a run tiles the
@@ -1069,21 +1085,22 @@ int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32
     CK(cudaEventRecord(done, st));
     CK(cudaStreamWaitEvent(cs, done, 0));
     const int n_run = s_end - run_start + 1;
-    const int32_t* a0 = add_idx0 + static_cast<size_t>(sub_first + run_start) * 3;
+    const int32_t* a0 = &anchors[static_cast<size_t>(run_start) * 3];
     for (int f = 0; f < (ctx->vel ? 2 : 1); ++f) {
       uint8_t* dsrc = static_cast<uint8_t*>(f == 0 ? ctx->d_disp : ctx->d_velo);
       uint8_t* hdst = static_cast<uint8_t*>(f == 0 ? disp_host : vel_host);
       for (int c = 0; c < 3; ++c) {
-        const size_t choff = static_cast<size_t>(c) * S0 * S1 * S2 * es;
+        uint8_t* dch = dsrc + static_cast<size_t>(c) * ND * plane_out;            // device slab channel
+        uint8_t* hch = hdst + (static_cast<size_t>(c) * S0 + dlo) * plane_out;    // same planes in the host box
         if (n_run == run_full) {
-          const size_t off = choff + static_cast<size_t>(a0[0]) * S1 * S2 * es;
-          CK(cudaMemcpyAsync(hdst + off, dsrc + off, static_cast<size_t>(crop[0]) * S1 * S2 * es, cudaMemcpyDeviceToHost, cs));
+          const size_t off = static_cast<size_t>(a0[0]) * plane_out;
+          CK(cudaMemcpyAsync(hch + off, dch + off, static_cast<size_t>(crop[0]) * plane_out, cudaMemcpyDeviceToHost, cs));
         } else {
           for (int s = run_start; s <= s_end; ++s) {
-            const int32_t* ai = add_idx0 + static_cast<size_t>(sub_first + s) * 3;
+            const int32_t* ai = &anchors[static_cast<size_t>(s) * 3];
             cudaMemcpy3DParms p3 = {};
-            p3.srcPtr = make_cudaPitchedPtr(dsrc + choff, S2 * es, S2, S1);
-            p3.dstPtr = make_cudaPitchedPtr(hdst + choff, S2 * es, S2, S1);
+            p3.srcPtr = make_cudaPitchedPtr(dch, S2 * es, S2, S1);
+            p3.dstPtr = make_cudaPitchedPtr(hch, S2 * es, S2, S1);
             p3.srcPos = make_cudaPos(static_cast<size_t>(ai[2]) * es, ai[1], ai[0]);
             p3.dstPos = p3.srcPos;
             p3.extent = make_cudaExtent(static_cast<size_t>(crop[2]) * es, crop[1], crop[0]);
@@ -1096,9 +1113,11 @@ int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32
     run_start = s_end + 1;
     return NBE_OK;
   };
-  rc = process_box_core(ctx, ctx->d_box, in_dtype, size, crop, plen, crop_idx, add_idx0, sub_first, sub_count, Dz, vel_fac,
-                        ctx->d_disp, ctx->d_velo, out_dtype, st, [&](int s) -> int {
-                          const int32_t* ai = add_idx0 + static_cast<size_t>(sub_first + s) * 3;
+  const int32_t size_in[3] = {static_cast<int32_t>(n_slots), size[1], size[2]};
+  const int32_t size_out[3] = {static_cast<int32_t>(ND), size[1], size[2]};
+  rc = process_box_core(ctx, ctx->d_box, in_dtype, size_in, size_out, crop, plen, tabs.data(), anchors.data(), 0, sub_count,
+                        Dz, vel_fac, ctx->d_disp, ctx->d_velo, out_dtype, st, [&](int s) -> int {
+                          const int32_t* ai = &anchors[static_cast<size_t>(s) * 3];
                           const bool last = s + 1 == sub_count;
                           const bool run_ends = last || (ai + 3)[0] != ai[0] || (s - run_start + 1) == run_full;
                           return run_ends ? flush_run(s) : NBE_OK;
