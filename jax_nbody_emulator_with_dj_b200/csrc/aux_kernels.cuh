@@ -25,7 +25,13 @@ struct EmitRule {
   int16_t row_base;   // row of output channel 0 inside the B stage
   int16_t kcol;       // column offset (16-channel rows only)
   int16_t alt_kd1;    // added to row_base for the taps with kd == 1 of a 3^3 conv (see acc3 layout)
+  // CTA-pair layout: a stage holds [CTA0 rows | CTA1 rows] (pair_rows each); output channel o of
+  // this rule lands in CTA (o / mod + cta_base) at row row_base + o % mod.  mod == 0: no split.
+  int16_t mod;
+  int8_t cta_base;
+  int8_t kd_mask;     // bit kd set: the rule applies to taps of that kd-plane (0: all)
 };
+constexpr int kMaxRules = 10;
 
 struct LayerMeta {
   const float* W;        // (cout, cin, k3) raw weight, or premodulated weight
@@ -46,7 +52,8 @@ struct LayerMeta {
   int n_rules;
   int row0;              // first block index (prefix sum of cout)
   int tap_tile[27];
-  EmitRule rules[6];
+  EmitRule rules[kMaxRules];
+  int pair_rows;         // rows per CTA in a pair-layout stage
 };
 
 __global__ void __launch_bounds__(128)
@@ -126,7 +133,10 @@ modulate_kernel(const LayerMeta* __restrict__ metas, int n_layers, const float* 
       const __half v = R.what == EMIT_WH ? wh : (R.what == EMIT_WL ? wl : dh);
       const long long tile = M.tap_tile[tap] + kc * M.kc_stride + R.kind * M.kind_stride;
       const int col = M.kc16 ? (R.kcol + i) : (i & 63);
-      const int row = R.row_base + ((M.k3 == 27 && tap / 9 == 1) ? R.alt_kd1 : 0) + o;
+      const int kd = M.k3 == 27 ? tap / 9 : 0;
+      if (R.kd_mask && !((R.kd_mask >> kd) & 1)) continue;
+      const int row = R.mod ? ((o / R.mod + R.cta_base) * M.pair_rows + R.row_base + o % R.mod)
+                            : (R.row_base + (kd == 1 ? R.alt_kd1 : 0) + o);
       M.dst[sample_off + (tile * M.nrs + row) * rowlen + col] = v;
     }
   }

@@ -119,12 +119,15 @@ __device__ __forceinline__ void store_from_f32(void* p, int64_t i, int dtype, fl
   else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
 }
 
-template <int NRS, int DC, int TM>
+constexpr int kPairRows = 96;      // B rows each CTA of a pair stages per tap (its halves of every op's rows)
+
+template <int NRS, int DC, int TM, bool PAIR = false>
 struct ConvCfg {
   static constexpr int kHRows = 16 * TM + 2;               // h-lines of one activation block
   static constexpr int kABlk = (kHRows * 10 * 128 + 1023) / 1024 * 1024;   // bytes, wide 64-channel block
   static constexpr int kAStage = 2 * kABlk;
-  static constexpr int kBStage = NRS * 128;
+  static constexpr int kBRows = PAIR ? kPairRows : NRS;     // rows this CTA stages per tap
+  static constexpr int kBStage = kBRows * 128;
   static constexpr int kNA = (TM == 1) ? 3 : 2;
   static constexpr int kCtrl = 2048;                       // barriers, TMEM slot, bias
   static constexpr int kBudget = kSmemLimit - 1024 /*align*/ - kCtrl - kNA * kAStage;
@@ -145,11 +148,11 @@ struct ConvCfg {
 #endif
 constexpr bool kBaseOffsetMode = NBE_BASE_OFFSET != 0;
 
-template <int NRS, int DC, int TM, bool FINAL>
+template <int NRS, int DC, int TM, bool FINAL, bool PAIR = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupTable gt,
                 const __grid_constant__ FinalArgs fa) {
-  using Cfg = ConvCfg<NRS, DC, TM>;
+  using Cfg = ConvCfg<NRS, DC, TM, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -169,6 +172,10 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int kIssuers = TM == 2 ? 2 : 1;
+  // CTA pair (cta_group::2): rank 0 is the leader; its barriers collect the TMA bytes of both
+  // CTAs and it alone issues the M = 256 MMAs, each CTA contributing its own 128 voxel rows and
+  // its half of every weight operand's rows
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
 
   const int n_groups = gt.n_groups;
   const int out_w = L->out_w, out_h = L->out_h, out_d = L->out_d;
@@ -182,10 +189,13 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     // barriers, so those expect kIssuers arrivals
     for (int i = 0; i < Cfg::kNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], kIssuers); }
     for (int i = 0; i < Cfg::kNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], kIssuers); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], kIssuers); mbar_init(&acc_empty[i], 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], kIssuers); mbar_init(&acc_empty[i], PAIR ? 512 : 256); }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   if (warp == 3) {
     const int nb = FINAL ? 16 : L->cout;
     for (int i = lane; i < nb; i += 32) bias_s[i] = L->bias[i];
@@ -207,9 +217,12 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     tmem_st_wait();
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
 
+  // a pair walks the item list two at a time (leader takes the even one); both CTAs of a pair
+  // therefore run the same number of iterations
+  const long long item_first = PAIR ? static_cast<long long>(blockIdx.x & ~1u) : static_cast<long long>(blockIdx.x);
   auto decode = [&](long long item, int& par, int& w0, int& h0, int& d0) {
     const int tw = static_cast<int>(item % tiles_w); item /= tiles_w;
     const int th = static_cast<int>(item % tiles_h); item /= tiles_h;
@@ -223,17 +236,24 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     // ------------------------------------------------ A producer (activation blocks)
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
-      for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (long long it0 = item_first; it0 < n_items; it0 += gridDim.x) {
+        const long long item = it0 + rank;
         int par, w0, h0, d0;
-        decode(item, par, w0, h0, d0);
+        decode(item < n_items ? item : 0, par, w0, h0, d0);
+        if (item >= n_items) d0 = out_d + 1024;        // idle half of the last pair: every load is out of bounds (zeros)
         for (int g = 0; g < n_groups; ++g) {
           const GroupDesc& G = gt.g[g];
           const uint32_t blk = static_cast<uint32_t>(Cfg::kHRows) * G.pitch * (G.kc16 ? 32u : 128u);
           mbar_wait(&a_empty[s], ph ^ 1);
-          mbar_expect_tx(&a_full[s], blk * G.n_a);
-          for (int q = 0; q < G.n_a; ++q)
-            tma_load_4d(a_smem + s * Cfg::kAStage + q * Cfg::kABlk, &L->amap[G.a_map[q]], &a_full[s],
-                        G.c0, w0 + G.dw, h0 + G.dh, d0 + G.dd);
+          if (!PAIR || rank == 0) mbar_expect_tx(&a_full[s], blk * G.n_a * (PAIR ? 2 : 1));
+          for (int q = 0; q < G.n_a; ++q) {
+            if constexpr (PAIR)
+              tma_load_4d_2sm(a_smem + s * Cfg::kAStage + q * Cfg::kABlk, &L->amap[G.a_map[q]], &a_full[s],
+                              G.c0, w0 + G.dw, h0 + G.dh, d0 + G.dd);
+            else
+              tma_load_4d(a_smem + s * Cfg::kAStage + q * Cfg::kABlk, &L->amap[G.a_map[q]], &a_full[s],
+                          G.c0, w0 + G.dw, h0 + G.dh, d0 + G.dd);
+          }
           if (++s == Cfg::kNA) { s = 0; ph ^= 1; }
         }
       }
@@ -242,18 +262,19 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     // ------------------------------------------------ B producer (weight tiles)
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
-      for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (long long it0 = item_first; it0 < n_items; it0 += gridDim.x) {
         int par, w0, h0, d0;
-        decode(item, par, w0, h0, d0);
+        decode(it0, par, w0, h0, d0);
         for (int g = 0; g < n_groups; ++g) {
           const GroupDesc& G = gt.g[g];
           const CUtensorMap* bm = G.kc16 ? &L->bmap16 : &L->bmap64;
-          const uint32_t bytes = G.kc16 ? NRS * 32 : NRS * 128;
-          const int row0 = G.brow0 + par * L->par_brow_step;
+          const uint32_t bytes = Cfg::kBRows * (G.kc16 ? 32u : 128u);
+          const int row0 = G.brow0 + par * L->par_brow_step + (PAIR ? static_cast<int>(rank) * kPairRows : 0);
           for (int j = 0; j < G.ntaps; ++j) {
             mbar_wait(&b_empty[s], ph ^ 1);
-            mbar_expect_tx(&b_full[s], bytes);
-            tma_load_2d(b_smem + s * Cfg::kBStage, bm, &b_full[s], 0, row0 + j * G.brow_step);
+            if (!PAIR || rank == 0) mbar_expect_tx(&b_full[s], bytes * (PAIR ? 2 : 1));
+            if constexpr (PAIR) tma_load_2d_2sm(b_smem + s * Cfg::kBStage, bm, &b_full[s], 0, row0 + j * G.brow_step);
+            else tma_load_2d(b_smem + s * Cfg::kBStage, bm, &b_full[s], 0, row0 + j * G.brow_step);
             if (++s == Cfg::kNB) { s = 0; ph ^= 1; }
           }
         }
@@ -266,10 +287,16 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     // warps issue, one per M-tile: the issue path (not the tensor pipe) was the limiter, and
     // tile-disjoint accumulators keep the result independent of the interleaving.
     const int my_tile = warp - 2;
-    constexpr uint32_t idesc_base = umma_idesc_f16(128, 0, false);
+    auto mma = [](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc) {
+      if constexpr (PAIR) umma_f16_2sm(d, ad, bd, id, acc); else umma_f16(d, ad, bd, id, acc);
+    };
+    auto commit = [](uint64_t* bar) {
+      if constexpr (PAIR) umma_commit_2sm(bar); else umma_commit(bar);
+    };
+    constexpr uint32_t idesc_base = umma_idesc_f16(PAIR ? 256 : 128, 0, false);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0, buf = 0, pacc = 0;
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (long long item = item_first; item < n_items && (!PAIR || rank == 0); item += gridDim.x) {
       mbar_wait(&acc_empty[buf], pacc ^ 1);
       tc_fence_after();
       for (int g = 0; g < n_groups; ++g) {
@@ -316,30 +343,30 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
 #pragma unroll
                 for (int o = 0; o < 3; ++o)
                   if (o < n_ops)
-                    umma_f16(d_tile + op_d[o], (static_cast<uint64_t>(a_hi) << 32) | (a_lo + op_a[o] + a_row),
-                             (static_cast<uint64_t>(bdesc_hi) << 32) | (b_lo + op_b[o]), op_i[o], 1u);
+                    mma(d_tile + op_d[o], (static_cast<uint64_t>(a_hi) << 32) | (a_lo + op_a[o] + a_row),
+                        (static_cast<uint64_t>(bdesc_hi) << 32) | (b_lo + op_b[o]), op_i[o], 1u);
               } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
 #pragma unroll
                   for (int o = 0; o < 3; ++o)
                     if (o < n_ops)
-                      umma_f16(d_tile + op_d[o],
-                               (static_cast<uint64_t>(a_hi) << 32) | (a_lo + op_a[o] + a_row + 2u * k),
-                               (static_cast<uint64_t>(bdesc_hi) << 32) | (b_lo + op_b[o] + 2u * k), op_i[o], 1u);
+                      mma(d_tile + op_d[o],
+                          (static_cast<uint64_t>(a_hi) << 32) | (a_lo + op_a[o] + a_row + 2u * k),
+                          (static_cast<uint64_t>(bdesc_hi) << 32) | (b_lo + op_b[o] + 2u * k), op_i[o], 1u);
                 }
               }
             }
-            umma_commit(&b_empty[sb]);
+            commit(&b_empty[sb]);
           }
           __syncwarp();
           if (++sb == Cfg::kNB) { sb = 0; pb ^= 1; }
         }
-        if (elect_one()) umma_commit(&a_empty[sa]);
+        if (elect_one()) commit(&a_empty[sa]);
         __syncwarp();
         if (++sa == Cfg::kNA) { sa = 0; pa ^= 1; }
       }
-      if (elect_one()) umma_commit(&acc_full[buf]);
+      if (elect_one()) commit(&acc_full[buf]);
       __syncwarp();
       if (++buf == Cfg::kNBuf) { buf = 0; pacc ^= 1; }
     }
@@ -351,9 +378,11 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     const int r = q * 32 + lane;                  // accumulator row
     const int eg = (warp - 4) >> 2;               // epilogue warp set 0 / 1
     uint32_t buf = 0, pacc = 0;
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (long long it0 = item_first; it0 < n_items; it0 += gridDim.x) {
+      const long long item = it0 + rank;
+      const bool item_ok = item < n_items;
       int par, w0, h0, d0;
-      decode(item, par, w0, h0, d0);
+      decode(item_ok ? item : 0, par, w0, h0, d0);
       mbar_wait(&acc_full[buf], pacc);
       tc_fence_after();
 #pragma unroll
@@ -362,7 +391,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (buf * TM + t) * DC;
         const int w = w0 + (r & 7);
         const int h = h0 + t * 16 + (r >> 3);
-        const bool valid = (w < out_w) && (h < out_h);
+        const bool valid = item_ok && (w < out_w) && (h < out_h);
         if constexpr (FINAL) {
           if (TM == 1 && eg != 0) continue;
           uint32_t v[16];
@@ -461,16 +490,17 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&acc_empty[buf]);
+      if constexpr (PAIR) mbar_arrive_leader(&acc_empty[buf]); else mbar_arrive(&acc_empty[buf]);
       if (++buf == Cfg::kNBuf) { buf = 0; pacc ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 

@@ -28,11 +28,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 enum ConvType { T_CONV3 = 0, T_SKIP1 = 1, T_DOWN = 2, T_UP = 3 };
-enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_COUNT };
-struct InstInfo { int nrs, dc, tm; bool fin; };
+enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_COUNT };
+struct InstInfo { int nrs, dc, tm; bool fin; bool pair = false; };
 const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32, 16, 2, true},
                                  {128, 64, 2, false},  {64, 64, 2, false},   {256, 128, 1, false},
-                                 {128, 256, 2, false}, {256, 512, 1, false}};
+                                 {128, 256, 2, false}, {256, 512, 1, false}, {2 * kPairRows, 256, 2, false, true}};
 
 // activation tensors of the net
 enum ActId {
@@ -96,6 +96,7 @@ struct nbe_ctx {
   bool have_params = false, premod = false, vel = true;
   float eps = 1e-8f;
   int precision = NBE_PREC_SPLIT;
+  bool pair = false;        // CTA pairs (cta_group::2) for the 64-output velocity launches (NBE_PAIR=1)
   bool wide = true;         // w-halo'd activation blocks serving 9 taps per load (NBE_WIDE=0 disables)
   std::vector<Layer> layers;
   std::map<std::string, int> lidx;
@@ -217,6 +218,12 @@ int build_static(nbe_ctx* ctx) {
   for (auto& s : ctx->sl)
     for (auto& p : s.parts)
       if (p.layer < 0) return fail(ctx, NBE_ERR_STATE, "layer missing for launch %s", s.name.c_str());
+  if (ctx->pair)        // 3^3 (+ folded skip) launches of the split-precision velocity net run on CTA pairs
+    for (auto& s : ctx->sl) {
+      bool ok = s.inst == I_128_256_2 && ctx->wide;
+      for (auto& p : s.parts) ok = ok && (p.type == T_CONV3 || p.type == T_SKIP1);
+      if (ok) s.inst = I_PAIR_128_256_2;
+    }
 
   // ---- weight layout: tiles, emit rules, LayerMeta
   const int nkind = (vel && split) ? 2 : 1;
@@ -265,6 +272,13 @@ int build_static(nbe_ctx* ctx) {
         ++nr;
       };
       const bool acc3 = vel && split && !ii.fin;
+      M.pair_rows = kPairRows;
+      auto prule = [&](int what, int kind, int kdmask, int cta_base, int mod, int base, int kcol = 0) {
+        EmitRule& R = M.rules[nr++];
+        R.what = static_cast<int8_t>(what); R.kind = static_cast<int8_t>(kind); R.row_base = static_cast<int16_t>(base);
+        R.kcol = static_cast<int16_t>(kcol); R.alt_kd1 = 0; R.mod = static_cast<int16_t>(mod);
+        R.cta_base = static_cast<int8_t>(cta_base); R.kd_mask = static_cast<int8_t>(kdmask);
+      };
       const int C = ly.cout;
       if (ii.fin) {
         if (vel) {
@@ -274,6 +288,17 @@ int build_static(nbe_ctx* ctx) {
           rule(EMIT_WH, 0, 0, 0);
           if (split) { rule(EMIT_WL, 0, 8, 0); rule(EMIT_WH, 0, 16, 0); }
         }
+      } else if (ii.pair && k16) {   // N = 128 rows [Wh.. | dW]: CTA0 stages the primal rows, CTA1 the tangent rows
+        prule(EMIT_WH, 0, 0, 0, 64, 0, 0); prule(EMIT_WH, 0, 0, 0, 64, 0, 3); prule(EMIT_WL, 0, 0, 0, 64, 0, 6);
+        prule(EMIT_DW, 0, 0, 1, 64, 0, 0);
+      } else if (ii.pair) {
+        // per-CTA stage rows: kd 0 [R0: 64 | R1: 32], kd 1 likewise, kd 2 [Wh half 32 | dW half 32],
+        // lo [Wl half 32 | Wh half 32]; non-3^3 terms (folded skip) use the kd 0 form
+        prule(EMIT_WH, 0, 0b001, 0, 64, 0);  prule(EMIT_DW, 0, 0b001, 1, 64, 0);      // kd0: xh*[Wh|dW] -> (y0, dy)
+        prule(EMIT_DW, 0, 0b010, 0, 64, 0);  prule(EMIT_WH, 0, 0b010, 1, 64, 0);      // kd1: xh*[dW|Wh] -> (dy, y1)
+        prule(EMIT_WH, 0, 0b011, 0, 32, 64);                                          // kd0/1: dx*Wh -> dy
+        prule(EMIT_WH, 0, 0b100, 0, 32, 0);  prule(EMIT_DW, 0, 0b100, 0, 32, 32);     // kd2
+        prule(EMIT_WL, 1, 0, 0, 32, 0);      prule(EMIT_WH, 1, 0, 0, 32, 32);         // lo products
       } else if (k16) {
         rule(EMIT_WH, 0, 0, 0); rule(EMIT_WH, 0, 0, 3); rule(EMIT_WL, 0, 0, 6);
         if (vel) rule(EMIT_DW, 0, C, 0);
@@ -448,8 +473,9 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
         amap[key] = n_amap;
         return n_amap++;
       };
-      if ((rc = make_b_map(ctx, &Lc.bmap64, packed + s.b64_off, 64, static_cast<long long>(s.n_tiles64) * ii.nrs, ii.nrs)) ||
-          (rc = make_b_map(ctx, &Lc.bmap16, packed + s.b16_off, 16, static_cast<long long>(s.n_tiles16) * ii.nrs, ii.nrs))) { delete P; return rc; }
+      const int box_rows = ii.pair ? kPairRows : ii.nrs;
+      if ((rc = make_b_map(ctx, &Lc.bmap64, packed + s.b64_off, 64, static_cast<long long>(s.n_tiles64) * ii.nrs, box_rows)) ||
+          (rc = make_b_map(ctx, &Lc.bmap16, packed + s.b16_off, 16, static_cast<long long>(s.n_tiles16) * ii.nrs, box_rows))) { delete P; return rc; }
 
       int ng = 0;
       bool bad = false;
@@ -483,6 +509,34 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
         auto fill_ops = [&](GroupDesc& G, int kind, const Src& sc, int par, int kd) {
           const bool acc3 = vel && split && !ii.fin && !k16;
           const __half* ph = hi(sc.act);
+          if (ii.pair) {      // CTA-pair operand layout (see build_static): b_row is a row of the per-CTA stage
+            G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par));
+            if (k16) {
+              G.n_a = 1; G.a_map[1] = -1; G.n_ops = 1;
+              G.ops[0] = OP(0, 2 * C / 8, 0, 0);
+            } else if (kind == 1) {
+              G.n_a = 2; G.a_map[1] = static_cast<int16_t>(get_map(lo(sc.act), sc.act, par)); G.n_ops = 2;
+              G.ops[0] = OP(0, C / 8, 0, 0);
+              G.ops[1] = OP(1, C / 8, 32, 0);
+            } else {
+              G.n_a = 2; G.a_map[1] = static_cast<int16_t>(get_map(dx(sc.act), sc.act, par));
+              if (kd == 1) {
+                G.n_ops = 2;
+                G.ops[0] = OP(0, 2 * C / 8, 0, C);
+                G.ops[1] = OP(1, C / 8, 64, C);
+              } else if (kd == 2) {
+                G.n_ops = 3;
+                G.ops[0] = OP(0, C / 8, 0, 3 * C);
+                G.ops[1] = OP(0, C / 8, 32, C);
+                G.ops[2] = OP(1, C / 8, 0, C);
+              } else {
+                G.n_ops = 2;
+                G.ops[0] = OP(0, 2 * C / 8, 0, 0);
+                G.ops[1] = OP(1, C / 8, 64, C);
+              }
+            }
+            return;
+          }
           if (k16) {
             G.n_a = 1; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par)); G.a_map[1] = -1;
             G.n_ops = 1;
@@ -613,6 +667,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
       }
       const long long tiles = 1ll * Lc.n_par * Lc.out_d * ((Lc.out_h + 16 * ii.tm - 1) / (16 * ii.tm)) * ((Lc.out_w + 7) / 8);
       H.grid = static_cast<int>(std::min<long long>(tiles, ctx->num_sms));
+      if (ii.pair) H.grid = 2 * static_cast<int>(std::min<long long>((tiles + 1) / 2, ctx->num_sms / 2));
     }
   }
   // upload
@@ -642,6 +697,25 @@ cudaError_t launch_inst(const ConvLaunch* dl, const GroupTable& gt, const FinalA
   return cudaGetLastError();
 }
 
+template <int NRS, int DC, int TM>
+cudaError_t launch_pair(const ConvLaunch* dl, const GroupTable& gt, const FinalArgs& fa, int grid, cudaStream_t st) {
+  using Cfg = ConvCfg<NRS, DC, TM, true>;
+  static bool attr_set = false;
+  auto kern = conv_mma_kernel<NRS, DC, TM, false, true>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, dl, gt, fa);
+}
+
 cudaError_t launch_conv(int inst, const ConvLaunch* dl, const GroupTable& gt, const FinalArgs& fa, int grid, cudaStream_t st) {
   switch (inst) {
     case I_128_128_2: return launch_inst<128, 128, 2, false>(dl, gt, fa, grid, st);
@@ -652,6 +726,7 @@ cudaError_t launch_conv(int inst, const ConvLaunch* dl, const GroupTable& gt, co
     case I_256_128_2: return launch_inst<256, 128, 1, false>(dl, gt, fa, grid, st);
     case I_128_256_2: return launch_inst<128, 256, 2, false>(dl, gt, fa, grid, st);
     case I_256_512_1: return launch_inst<256, 512, 1, false>(dl, gt, fa, grid, st);
+    case I_PAIR_128_256_2: return launch_pair<2 * kPairRows, 256, 2>(dl, gt, fa, grid, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -808,6 +883,7 @@ int nbe_create(nbe_ctx** out, int device) {
   }
   ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
   if (const char* e = getenv("NBE_WIDE")) ctx->wide = atoi(e) != 0;
+  if (const char* e = getenv("NBE_PAIR")) ctx->pair = atoi(e) != 0;
   cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   *out = ctx;
