@@ -119,14 +119,14 @@ __device__ __forceinline__ void store_from_f32(void* p, int64_t i, int dtype, fl
   else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
 }
 
-constexpr int kPairRows = 96;      // B rows each CTA of a pair stages per tap (its halves of every op's rows)
 
 template <int NRS, int DC, int TM, bool PAIR = false>
 struct ConvCfg {
   static constexpr int kHRows = 16 * TM + 2;               // h-lines of one activation block
   static constexpr int kABlk = (kHRows * 10 * 128 + 1023) / 1024 * 1024;   // bytes, wide 64-channel block
   static constexpr int kAStage = 2 * kABlk;
-  static constexpr int kBRows = PAIR ? kPairRows : NRS;     // rows this CTA stages per tap
+  // pair mode: NRS counts the rows of BOTH CTAs; each stages its halves of every op's rows
+  static constexpr int kBRows = PAIR ? NRS / 2 : NRS;       // rows this CTA stages per tap
   static constexpr int kBStage = kBRows * 128;
   static constexpr int kNA = (TM == 1) ? 3 : 2;
   static constexpr int kCtrl = 2048;                       // barriers, TMEM slot, bias
@@ -269,7 +269,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
           const GroupDesc& G = gt.g[g];
           const CUtensorMap* bm = G.kc16 ? &L->bmap16 : &L->bmap64;
           const uint32_t bytes = Cfg::kBRows * (G.kc16 ? 32u : 128u);
-          const int row0 = G.brow0 + par * L->par_brow_step + (PAIR ? static_cast<int>(rank) * kPairRows : 0);
+          const int row0 = G.brow0 + par * L->par_brow_step + (PAIR ? static_cast<int>(rank) * Cfg::kBRows : 0);
           for (int j = 0; j < G.ntaps; ++j) {
             mbar_wait(&b_empty[s], ph ^ 1);
             if (!PAIR || rank == 0) mbar_expect_tx(&b_full[s], bytes * (PAIR ? 2 : 1));

@@ -28,11 +28,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 enum ConvType { T_CONV3 = 0, T_SKIP1 = 1, T_DOWN = 2, T_UP = 3 };
-enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_COUNT };
+enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_PAIR_256_512_1, I_PAIR_128_128_2, I_PAIR_256_256_1, I_COUNT };
 struct InstInfo { int nrs, dc, tm; bool fin; bool pair = false; };
 const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32, 16, 2, true},
                                  {128, 64, 2, false},  {64, 64, 2, false},   {256, 128, 1, false},
-                                 {128, 256, 2, false}, {256, 512, 1, false}, {2 * kPairRows, 256, 2, false, true}};
+                                 {128, 256, 2, false}, {256, 512, 1, false},
+                                 // CTA-pair instances: nrs = rows of both CTAs = 2 x 1.5 x Cout
+                                 {192, 256, 2, false, true}, {384, 512, 1, false, true}, {192, 128, 2, false, true}, {384, 256, 1, false, true}};
 
 // activation tensors of the net
 enum ActId {
@@ -96,7 +98,7 @@ struct nbe_ctx {
   bool have_params = false, premod = false, vel = true;
   float eps = 1e-8f;
   int precision = NBE_PREC_SPLIT;
-  bool pair = false;        // CTA pairs (cta_group::2) for the 64-output velocity launches (NBE_PAIR=1)
+  bool pair = true;         // CTA pairs (cta_group::2) for the 3^3 velocity launches (NBE_PAIR=0 disables)
   bool wide = true;         // w-halo'd activation blocks serving 9 taps per load (NBE_WIDE=0 disables)
   std::vector<Layer> layers;
   std::map<std::string, int> lidx;
@@ -220,9 +222,13 @@ int build_static(nbe_ctx* ctx) {
       if (p.layer < 0) return fail(ctx, NBE_ERR_STATE, "layer missing for launch %s", s.name.c_str());
   if (ctx->pair)        // 3^3 (+ folded skip) launches of the split-precision velocity net run on CTA pairs
     for (auto& s : ctx->sl) {
-      bool ok = s.inst == I_128_256_2 && ctx->wide;
+      bool ok = ctx->wide && vel;
       for (auto& p : s.parts) ok = ok && (p.type == T_CONV3 || p.type == T_SKIP1);
-      if (ok) s.inst = I_PAIR_128_256_2;
+      if (!ok) continue;
+      if (s.inst == I_128_256_2) s.inst = I_PAIR_128_256_2;
+      else if (s.inst == I_256_512_1) s.inst = I_PAIR_256_512_1;
+      else if (s.inst == I_128_128_2) s.inst = I_PAIR_128_128_2;
+      else if (s.inst == I_256_256_1) s.inst = I_PAIR_256_256_1;
     }
 
   // ---- weight layout: tiles, emit rules, LayerMeta
@@ -272,7 +278,7 @@ int build_static(nbe_ctx* ctx) {
         ++nr;
       };
       const bool acc3 = vel && split && !ii.fin;
-      M.pair_rows = kPairRows;
+      M.pair_rows = ii.nrs / 2;
       auto prule = [&](int what, int kind, int kdmask, int cta_base, int mod, int base, int kcol = 0) {
         EmitRule& R = M.rules[nr++];
         R.what = static_cast<int8_t>(what); R.kind = static_cast<int8_t>(kind); R.row_base = static_cast<int16_t>(base);
@@ -288,17 +294,19 @@ int build_static(nbe_ctx* ctx) {
           rule(EMIT_WH, 0, 0, 0);
           if (split) { rule(EMIT_WL, 0, 8, 0); rule(EMIT_WH, 0, 16, 0); }
         }
-      } else if (ii.pair && k16) {   // N = 128 rows [Wh.. | dW]: CTA0 stages the primal rows, CTA1 the tangent rows
-        prule(EMIT_WH, 0, 0, 0, 64, 0, 0); prule(EMIT_WH, 0, 0, 0, 64, 0, 3); prule(EMIT_WL, 0, 0, 0, 64, 0, 6);
-        prule(EMIT_DW, 0, 0, 1, 64, 0, 0);
-      } else if (ii.pair) {
-        // per-CTA stage rows: kd 0 [R0: 64 | R1: 32], kd 1 likewise, kd 2 [Wh half 32 | dW half 32],
-        // lo [Wl half 32 | Wh half 32]; non-3^3 terms (folded skip) use the kd 0 form
-        prule(EMIT_WH, 0, 0b001, 0, 64, 0);  prule(EMIT_DW, 0, 0b001, 1, 64, 0);      // kd0: xh*[Wh|dW] -> (y0, dy)
-        prule(EMIT_DW, 0, 0b010, 0, 64, 0);  prule(EMIT_WH, 0, 0b010, 1, 64, 0);      // kd1: xh*[dW|Wh] -> (dy, y1)
-        prule(EMIT_WH, 0, 0b011, 0, 32, 64);                                          // kd0/1: dx*Wh -> dy
-        prule(EMIT_WH, 0, 0b100, 0, 32, 0);  prule(EMIT_DW, 0, 0b100, 0, 32, 32);     // kd2
-        prule(EMIT_WL, 1, 0, 0, 32, 0);      prule(EMIT_WH, 1, 0, 0, 32, 32);         // lo products
+      } else if (ii.pair && k16) {   // N = 2C rows [Wh.. | dW]: CTA0 stages the primal rows, CTA1 the tangent rows
+        prule(EMIT_WH, 0, 0, 0, C, 0, 0); prule(EMIT_WH, 0, 0, 0, C, 0, 3); prule(EMIT_WL, 0, 0, 0, C, 0, 6);
+        prule(EMIT_DW, 0, 0, 1, C, 0, 0);
+      } else if (ii.pair && acc3) {
+        // per-CTA stage rows: kd 0 / kd 1 [R0: C | R1: C/2], kd 2 [Wh half | dW half],
+        // lo [Wl half | Wh half]; non-3^3 terms (folded skip) use the kd 0 form
+        prule(EMIT_WH, 0, 0b001, 0, C, 0);      prule(EMIT_DW, 0, 0b001, 1, C, 0);         // kd0: xh*[Wh|dW] -> (y0, dy)
+        prule(EMIT_DW, 0, 0b010, 0, C, 0);      prule(EMIT_WH, 0, 0b010, 1, C, 0);         // kd1: xh*[dW|Wh] -> (dy, y1)
+        prule(EMIT_WH, 0, 0b011, 0, C / 2, C);                                             // kd0/1: dx*Wh -> dy
+        prule(EMIT_WH, 0, 0b100, 0, C / 2, 0);  prule(EMIT_DW, 0, 0b100, 0, C / 2, C / 2); // kd2
+        prule(EMIT_WL, 1, 0, 0, C / 2, 0);      prule(EMIT_WH, 1, 0, 0, C / 2, C / 2);     // lo products
+      } else if (ii.pair) {          // single-product velocity: [R0: Wh|dW halves (C) | R1: Wh halves (C/2)]
+        prule(EMIT_WH, 0, 0, 0, C, 0); prule(EMIT_DW, 0, 0, 1, C, 0); prule(EMIT_WH, 0, 0, 0, C / 2, C);
       } else if (k16) {
         rule(EMIT_WH, 0, 0, 0); rule(EMIT_WH, 0, 0, 3); rule(EMIT_WL, 0, 0, 6);
         if (vel) rule(EMIT_DW, 0, C, 0);
@@ -473,7 +481,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
         amap[key] = n_amap;
         return n_amap++;
       };
-      const int box_rows = ii.pair ? kPairRows : ii.nrs;
+      const int box_rows = ii.pair ? ii.nrs / 2 : ii.nrs;
       if ((rc = make_b_map(ctx, &Lc.bmap64, packed + s.b64_off, 64, static_cast<long long>(s.n_tiles64) * ii.nrs, box_rows)) ||
           (rc = make_b_map(ctx, &Lc.bmap16, packed + s.b16_off, 16, static_cast<long long>(s.n_tiles16) * ii.nrs, box_rows))) { delete P; return rc; }
 
@@ -517,22 +525,22 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
             } else if (kind == 1) {
               G.n_a = 2; G.a_map[1] = static_cast<int16_t>(get_map(lo(sc.act), sc.act, par)); G.n_ops = 2;
               G.ops[0] = OP(0, C / 8, 0, 0);
-              G.ops[1] = OP(1, C / 8, 32, 0);
+              G.ops[1] = OP(1, C / 8, C / 2, 0);
             } else {
               G.n_a = 2; G.a_map[1] = static_cast<int16_t>(get_map(dx(sc.act), sc.act, par));
-              if (kd == 1) {
+              if (acc3 && kd == 1) {
                 G.n_ops = 2;
                 G.ops[0] = OP(0, 2 * C / 8, 0, C);
-                G.ops[1] = OP(1, C / 8, 64, C);
-              } else if (kd == 2) {
+                G.ops[1] = OP(1, C / 8, C, C);
+              } else if (acc3 && kd == 2) {
                 G.n_ops = 3;
                 G.ops[0] = OP(0, C / 8, 0, 3 * C);
-                G.ops[1] = OP(0, C / 8, 32, C);
+                G.ops[1] = OP(0, C / 8, C / 2, C);
                 G.ops[2] = OP(1, C / 8, 0, C);
               } else {
                 G.n_ops = 2;
                 G.ops[0] = OP(0, 2 * C / 8, 0, 0);
-                G.ops[1] = OP(1, C / 8, 64, C);
+                G.ops[1] = OP(1, C / 8, C, C);
               }
             }
             return;
@@ -726,7 +734,10 @@ cudaError_t launch_conv(int inst, const ConvLaunch* dl, const GroupTable& gt, co
     case I_256_128_2: return launch_inst<256, 128, 1, false>(dl, gt, fa, grid, st);
     case I_128_256_2: return launch_inst<128, 256, 2, false>(dl, gt, fa, grid, st);
     case I_256_512_1: return launch_inst<256, 512, 1, false>(dl, gt, fa, grid, st);
-    case I_PAIR_128_256_2: return launch_pair<2 * kPairRows, 256, 2>(dl, gt, fa, grid, st);
+    case I_PAIR_128_256_2: return launch_pair<192, 256, 2>(dl, gt, fa, grid, st);
+    case I_PAIR_256_512_1: return launch_pair<384, 512, 1>(dl, gt, fa, grid, st);
+    case I_PAIR_128_128_2: return launch_pair<192, 128, 2>(dl, gt, fa, grid, st);
+    case I_PAIR_256_256_1: return launch_pair<384, 256, 1>(dl, gt, fa, grid, st);
   }
   return cudaErrorInvalidValue;
 }
