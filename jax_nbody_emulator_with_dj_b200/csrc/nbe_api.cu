@@ -29,12 +29,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 enum ConvType { T_CONV3 = 0, T_SKIP1 = 1, T_DOWN = 2, T_UP = 3 };
 enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_PAIR_256_512_1, I_PAIR_128_128_2, I_PAIR_256_256_1, I_COUNT };
-struct InstInfo { int nrs, dc, tm; bool fin; bool pair = false; };
+struct InstInfo { int nrs, dc, tm; bool fin; bool pair = false; bool acc3 = false; };
 const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32, 16, 2, true},
                                  {128, 64, 2, false},  {64, 64, 2, false},   {256, 128, 1, false},
-                                 {128, 256, 2, false}, {256, 512, 1, false},
+                                 {128, 256, 2, false, false, true}, {256, 512, 1, false, false, true},
                                  // CTA-pair instances: nrs = rows of both CTAs = 2 x 1.5 x Cout
-                                 {192, 256, 2, false, true}, {384, 512, 1, false, true}, {192, 128, 2, false, true}, {384, 256, 1, false, true}};
+                                 {192, 256, 2, false, true, true}, {384, 512, 1, false, true, true},
+                                 {192, 128, 2, false, true}, {384, 256, 1, false, true}};
 
 // activation tensors of the net
 enum ActId {
@@ -220,6 +221,15 @@ int build_static(nbe_ctx* ctx) {
   for (auto& s : ctx->sl)
     for (auto& p : s.parts)
       if (p.layer < 0) return fail(ctx, NBE_ERR_STATE, "layer missing for launch %s", s.name.c_str());
+  // one primal accumulator per kd only where it matters (27-tap convs over 64-channel inputs); the
+  // K = 16 first layer and the 1- / 8-tap resampling layers accumulate few terms and keep the
+  // double-buffered single-accumulator instances (epilogue overlapped with the next item's MMAs)
+  for (auto& s : ctx->sl) {
+    bool deep = false;
+    for (auto& p : s.parts) deep = deep || (p.type == T_CONV3 && !p.src[0].kc16);
+    if (!deep && s.inst == I_128_256_2) s.inst = I_128_128_2;
+    if (!deep && s.inst == I_256_512_1) s.inst = I_256_256_1;
+  }
   if (ctx->pair)        // 3^3 (+ folded skip) launches of the split-precision velocity net run on CTA pairs
     for (auto& s : ctx->sl) {
       bool ok = ctx->wide && vel;
@@ -277,7 +287,7 @@ int build_static(nbe_ctx* ctx) {
         M.rules[nr].alt_kd1 = static_cast<int16_t>(alt);
         ++nr;
       };
-      const bool acc3 = vel && split && !ii.fin;
+      const bool acc3 = ii.acc3;
       M.pair_rows = ii.nrs / 2;
       auto prule = [&](int what, int kind, int kdmask, int cta_base, int mod, int base, int kcol = 0) {
         EmitRule& R = M.rules[nr++];
@@ -515,7 +525,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           return o;
         };
         auto fill_ops = [&](GroupDesc& G, int kind, const Src& sc, int par, int kd) {
-          const bool acc3 = vel && split && !ii.fin && !k16;
+          const bool acc3 = ii.acc3 && !k16;
           const __half* ph = hi(sc.act);
           if (ii.pair) {      // CTA-pair operand layout (see build_static): b_row is a row of the per-CTA stage
             G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par));
@@ -656,7 +666,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
       if (bad) { delete P; return fail(ctx, NBE_ERR_STATE, "launch %s: too many groups / tensor maps", s.name.c_str()); }
       H.G.n_groups = ng;
       Lc.cout = s.cout; Lc.vel = vel ? 1 : 0; Lc.act = 1;
-      Lc.acc3 = (vel && split && !ii.fin) ? 1 : 0;
+      Lc.acc3 = ii.acc3 ? 1 : 0;
       Lc.bias = ctx->d_bias + s.bias_off;
       if (!ii.fin) {
         Lc.out_h_ptr = hi(s.out_act);
