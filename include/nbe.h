@@ -137,11 +137,6 @@ int nbe_get_profile(nbe_ctx* ctx, int cap, const char** names, float* ms, double
  * 2 tangent) of the most recent plan.  host == NULL queries the size.                     */
 long long nbe_debug_read_act(nbe_ctx* ctx, int act, int which, void* host, size_t cap, int32_t shape_out[4]);
 
-/* Hardware self-test of the tcgen05 / TMA building blocks (descriptor encodings, swizzle
- * modes, row-shifted operand starts).  Writes a human-readable report; returns 0 if the
- * mandatory checks pass.                                                                 */
-int nbe_selftest(nbe_ctx* ctx, char* report, size_t report_cap);
-
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,7 @@ EXPORTS = (
     "nbe_create", "nbe_destroy", "nbe_last_error", "nbe_version", "nbe_set_params", "nbe_set_precision",
     "nbe_modulate", "nbe_get_modulated", "nbe_forward", "nbe_process_box", "nbe_process_box_dev",
     "nbe_workspace_bytes", "nbe_host_register", "nbe_host_unregister",
-    "nbe_launch_count", "nbe_set_profiling", "nbe_get_profile", "nbe_selftest", "nbe_debug_read_act",
+    "nbe_launch_count", "nbe_set_profiling", "nbe_get_profile", "nbe_debug_read_act",
 )
 
 
@@ -94,7 +94,6 @@ def load():
         lib.nbe_launch_count.restype = C.c_int64
         lib.nbe_set_profiling.argtypes = [vp, C.c_int]
         lib.nbe_get_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), f32p, C.POINTER(C.c_double)]
-        lib.nbe_selftest.argtypes = [vp, C.c_char_p, C.c_size_t]
         lib.nbe_debug_read_act.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t, i32p]
         lib.nbe_debug_read_act.restype = C.c_longlong
         for name in EXPORTS:

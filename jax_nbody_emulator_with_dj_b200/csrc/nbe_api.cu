@@ -1301,10 +1301,4 @@ long long nbe_debug_read_act(nbe_ctx* ctx, int act, int which, void* host, size_
   return static_cast<long long>(bytes);
 }
 
-int nbe_selftest(nbe_ctx* ctx, char* report, size_t report_cap) {
-  if (!ctx) return NBE_ERR_ARG;
-  if (report && report_cap) snprintf(report, report_cap, "selftest: see tests (conv parity vs CPU oracle)\n");
-  return NBE_OK;
-}
-
 }  // extern "C"
