@@ -100,9 +100,12 @@ modulate_kernel(const LayerMeta* __restrict__ metas, int n_layers, const float* 
   const float inv_Dz = 1.f / (s1 + 1.f);
   const long long sample_off = static_cast<long long>(b) * M.dst_sample_stride;
   const int rowlen = M.kc16 ? 16 : 64;
-  for (int e = threadIdx.x; e < ne; e += blockDim.x) {
-    const int i = e / M.k3;
-    const int tap = e - i * M.k3;
+  // emission loop: input channel fastest, so that consecutive threads write consecutive
+  // columns of one operand row (coalesced 2-byte stores); the weight row itself is L1-resident
+  for (int e2 = threadIdx.x; e2 < ne; e2 += blockDim.x) {
+    const int tap = e2 / M.cin;
+    const int i = e2 - tap * M.cin;
+    const int e = i * M.k3 + tap;
     float wn, dwn = 0.f;
     if (M.premod) {
       wn = Wrow[e];
