@@ -171,7 +171,7 @@ class SubboxProcessor:
         return self._merged[1], self._merged[2]
 
     def process_box(self, input_box, z, Om, desc="Processing subboxes", show_progress=True,
-                    shard=None, gather="all", copy=True, merge=None):
+                    shard=None, gather="all", copy=True, merge=None, out=None):
         """Process the whole box; returns displacement (C,D,H,W) or (displacement, velocity) as
         numpy arrays of ``config.output_dtype``.
 
@@ -182,6 +182,9 @@ class SubboxProcessor:
         processor's pinned output buffers, valid until the next call (saves a host memcpy).
         merge: e.g. (2, 2, 1) processes 2x2x1 reference subboxes as one larger tile (bit-identical
         output, fewer halo FLOPs, more activation memory).
+        out: (disp, vel) or disp -- caller-provided C-contiguous arrays of shape (C,)+size and
+        output_dtype (e.g. np.memmap for boxes that do not fit in RAM; input_box may be a memmap
+        too).  Only the voxels owned by this rank's subboxes are written; nothing is zeroed.
         """
         cfg = self.config
         tables = None
@@ -218,14 +221,24 @@ class SubboxProcessor:
         crop_idx, add0, plen = tables
 
         shape = (cfg.in_chan,) + tuple(cfg.size)
-        dis, vel = self._outputs(shape, out_np)
-        # voxels not owned by [lo, hi) must read zero: the cached buffers only need clearing when
-        # the owned range differs from the previous call's (owned blocks are always overwritten)
-        if self._out_range not in (None, (lo, hi)):
-            dis.fill(0)
-            if vel is not None:
-                vel.fill(0)
-        self._out_range = (lo, hi)
+        if out is not None:
+            outs = out if isinstance(out, (tuple, list)) else (out,)
+            if len(outs) != (2 if self.compute_vel else 1):
+                raise ValueError("out must be (disp, vel) for velocity models and disp otherwise")
+            for a in outs:
+                if a.shape != shape or a.dtype != out_np or not a.flags["C_CONTIGUOUS"]:
+                    raise ValueError(f"out arrays must be C-contiguous {shape} of {out_np}")
+            dis, vel = outs[0], (outs[1] if self.compute_vel else None)
+            copy = False
+        else:
+            dis, vel = self._outputs(shape, out_np)
+            # voxels not owned by [lo, hi) must read zero: the cached buffers only need clearing when
+            # the owned range differs from the previous call's (owned blocks are always overwritten)
+            if self._out_range not in (None, (lo, hi)):
+                dis.fill(0)
+                if vel is not None:
+                    vel.fill(0)
+            self._out_range = (lo, hi)
         self._pin_input(eng, box)
         bar = None
         if show_progress:
