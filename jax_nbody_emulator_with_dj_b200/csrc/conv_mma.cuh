@@ -47,6 +47,8 @@ struct GroupDesc {
   int16_t c0;         // channel coordinate of the box
   int8_t dw, dh, dd;  // block origin relative to the tile origin
   int8_t pitch;       // rows per h-line of the block: 8, or 10 (w-halo'd "wide" block, kw taps by row shift)
+  int8_t tps;         // taps per weight stage: 1, or 3 for 16-channel rows (three small tiles share a stage)
+  int8_t pad_[3];
   int32_t brow0;      // B row of tap 0
   int32_t brow_step;  // B rows between consecutive taps
   MmaOp ops[3];
@@ -77,6 +79,7 @@ struct alignas(128) ConvLaunch {
   int32_t vel;              // accumulator holds [y | dy]
   int32_t act;              // LeakyReLU
   int32_t acc3;             // accumulator columns are [y0 | dy | y1 | y2] (one primal accumulator per kd)
+  int32_t band_h;           // item order: bands of band_h tile rows, d swept inside a band (0: whole planes)
 };
 
 // Per-call arguments of the last layer's fused model tail.
@@ -132,7 +135,7 @@ struct ConvCfg {
   static constexpr int kCtrl = 2048;                       // barriers, TMEM slot, bias
   static constexpr int kBudget = kSmemLimit - 1024 /*align*/ - kCtrl - kNA * kAStage;
   static constexpr int kNBraw = kBudget / kBStage;
-  static constexpr int kNB = kNBraw > 6 ? 6 : kNBraw;
+  static constexpr int kNB = kNBraw > 12 ? 12 : kNBraw;
   static constexpr int kNBuf = (2 * TM * DC <= 512) ? 2 : 1;
   static constexpr int kColsRaw = kNBuf * TM * DC;
   static constexpr int kTmemCols = kColsRaw <= 32 ? 32 : kColsRaw <= 64 ? 64 : kColsRaw <= 128 ? 128
@@ -223,12 +226,25 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
   // a pair walks the item list two at a time (leader takes the even one); both CTAs of a pair
   // therefore run the same number of iterations
   const long long item_first = PAIR ? static_cast<long long>(blockIdx.x & ~1u) : static_cast<long long>(blockIdx.x);
+  // Item order (slowest to fastest): parity, h-band, d, tile row inside the band, tile column.
+  // The CTAs in flight then cover a narrow band over several d planes, so the three input planes
+  // a 3^3 tap window re-reads stay L2-resident between their uses.
+  const int band_h = (L->band_h > 0 && L->band_h < tiles_h) ? L->band_h : tiles_h;
+  const long long per_par = 1ll * out_d * tiles_h * tiles_w;
+  const long long band_items = 1ll * out_d * band_h * tiles_w;
+  const int n_bands = (tiles_h + band_h - 1) / band_h;
   auto decode = [&](long long item, int& par, int& w0, int& h0, int& d0) {
-    const int tw = static_cast<int>(item % tiles_w); item /= tiles_w;
-    const int th = static_cast<int>(item % tiles_h); item /= tiles_h;
-    d0 = static_cast<int>(item % out_d);
-    par = static_cast<int>(item / out_d);
-    w0 = tw * 8;
+    par = static_cast<int>(item / per_par);
+    long long r = item - par * per_par;
+    int band = static_cast<int>(r / band_items);
+    if (band > n_bands - 1) band = n_bands - 1;
+    r -= band * band_items;
+    const int bh = min(band_h, tiles_h - band * band_h);
+    const int plane = bh * tiles_w;
+    d0 = static_cast<int>(r / plane);
+    const int r3 = static_cast<int>(r - static_cast<long long>(d0) * plane);
+    const int th = band * band_h + r3 / tiles_w;
+    w0 = (r3 % tiles_w) * 8;
     h0 = th * 16 * TM;
   };
 
@@ -262,6 +278,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     // ------------------------------------------------ B producer (weight tiles)
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
+      const int par_brow_step = L->par_brow_step;
       for (long long it0 = item_first; it0 < n_items; it0 += gridDim.x) {
         int par, w0, h0, d0;
         decode(it0, par, w0, h0, d0);
@@ -269,12 +286,16 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
           const GroupDesc& G = gt.g[g];
           const CUtensorMap* bm = G.kc16 ? &L->bmap16 : &L->bmap64;
           const uint32_t bytes = Cfg::kBRows * (G.kc16 ? 32u : 128u);
-          const int row0 = G.brow0 + par * L->par_brow_step + (PAIR ? static_cast<int>(rank) * Cfg::kBRows : 0);
-          for (int j = 0; j < G.ntaps; ++j) {
+          const int row0 = G.brow0 + par * par_brow_step + (PAIR ? static_cast<int>(rank) * Cfg::kBRows : 0);
+          const int tps = G.tps;
+          for (int j = 0; j < G.ntaps; j += tps) {
             mbar_wait(&b_empty[s], ph ^ 1);
-            if (!PAIR || rank == 0) mbar_expect_tx(&b_full[s], bytes * (PAIR ? 2 : 1));
-            if constexpr (PAIR) tma_load_2d_2sm(b_smem + s * Cfg::kBStage, bm, &b_full[s], 0, row0 + j * G.brow_step);
-            else tma_load_2d(b_smem + s * Cfg::kBStage, bm, &b_full[s], 0, row0 + j * G.brow_step);
+            if (!PAIR || rank == 0) mbar_expect_tx(&b_full[s], bytes * tps * (PAIR ? 2 : 1));
+            for (int t = 0; t < tps; ++t) {
+              uint8_t* dst = b_smem + s * Cfg::kBStage + t * bytes;
+              if constexpr (PAIR) tma_load_2d_2sm(dst, bm, &b_full[s], 0, row0 + (j + t) * G.brow_step);
+              else tma_load_2d(dst, bm, &b_full[s], 0, row0 + (j + t) * G.brow_step);
+            }
             if (++s == Cfg::kNB) { s = 0; ph ^= 1; }
           }
         }
@@ -322,10 +343,15 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
         mbar_wait(&a_full[sa], pa);
         tc_fence_after();
         const uint32_t a_lo = ((smem_u32(a_smem + sa * Cfg::kAStage) & 0x3FFFFu) >> 4) | (1u << 16);
-        for (int j = 0; j < ntaps; ++j) {
-          mbar_wait(&b_full[sb], pb);
-          tc_fence_after();
-          const uint32_t b_lo = ((smem_u32(b_smem + sb * Cfg::kBStage) & 0x3FFFFu) >> 4) | (1u << 16);
+        const int tps = G.tps;
+        const uint32_t tap16 = static_cast<uint32_t>(Cfg::kBRows) * row16;   // one tap's tile in 16-byte units
+        for (int j = 0, jt = 0; j < ntaps; ++j) {
+          if (jt == 0) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+          }
+          const uint32_t b_lo =
+              (((smem_u32(b_smem + sb * Cfg::kBStage) & 0x3FFFFu) >> 4) + static_cast<uint32_t>(jt) * tap16) | (1u << 16);
           if (elect_one()) {
 #pragma unroll
             for (int t = 0; t < TM; ++t) {
@@ -357,10 +383,13 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
                 }
               }
             }
-            commit(&b_empty[sb]);
+            if (jt == tps - 1) commit(&b_empty[sb]);
           }
           __syncwarp();
-          if (++sb == Cfg::kNB) { sb = 0; pb ^= 1; }
+          if (++jt == tps) {
+            jt = 0;
+            if (++sb == Cfg::kNB) { sb = 0; pb ^= 1; }
+          }
         }
         if (elect_one()) commit(&a_empty[sa]);
         __syncwarp();
@@ -377,6 +406,17 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     const int q = warp & 3;                       // TMEM lane quarter of this warp
     const int r = q * 32 + lane;                  // accumulator row
     const int eg = (warp - 4) >> 2;               // epilogue warp set 0 / 1
+    // launch fields are read once: the asm memory clobbers below would otherwise make every item
+    // re-load them from global memory (a ~1 us dependent stall per item in the ncu source view)
+    const int cout = L->cout;
+    const bool vel = L->vel != 0;
+    const bool act = L->act != 0;
+    const bool acc3 = L->acc3 != 0;
+    const int64_t out_sw = L->out_sw, out_sh = L->out_sh, out_sd = L->out_sd;
+    const int64_t par_ow = L->par_ow, par_oh = L->par_oh, par_od = L->par_od;
+    __half* const out_h_ptr = L->out_h_ptr;
+    __half* const out_l_ptr = L->out_l_ptr;
+    __half* const out_d_ptr = L->out_d_ptr;
     uint32_t buf = 0, pacc = 0;
     for (long long it0 = item_first; it0 < n_items; it0 += gridDim.x) {
       const long long item = it0 + rank;
@@ -419,17 +459,12 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
             }
           }
         } else {
-          const int cout = L->cout;
-          const bool vel = L->vel != 0;
-          const bool act = L->act != 0;
-          const bool acc3 = L->acc3 != 0;
           const int pc = par & 1, pb2 = (par >> 1) & 1, pa2 = (par >> 2) & 1;
-          const int64_t voff = static_cast<int64_t>(d0) * L->out_sd + static_cast<int64_t>(h) * L->out_sh +
-                               static_cast<int64_t>(w) * L->out_sw + pc * L->par_ow + pb2 * L->par_oh +
-                               pa2 * L->par_od;
-          __half* oh = L->out_h_ptr + voff;
-          __half* ol = L->out_l_ptr ? L->out_l_ptr + voff : nullptr;
-          __half* od = L->out_d_ptr ? L->out_d_ptr + voff : nullptr;
+          const int64_t voff = static_cast<int64_t>(d0) * out_sd + static_cast<int64_t>(h) * out_sh +
+                               static_cast<int64_t>(w) * out_sw + pc * par_ow + pb2 * par_oh + pa2 * par_od;
+          __half* oh = out_h_ptr + voff;
+          __half* ol = out_l_ptr ? out_l_ptr + voff : nullptr;
+          __half* od = out_d_ptr ? out_d_ptr + voff : nullptr;
           for (int c = (TM == 1 ? eg * 32 : 0); c < cout; c += (TM == 1 ? 64 : 32)) {
             uint32_t y[32], dy[32];
             tmem_ld32(taddr + c, y);

@@ -28,14 +28,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 enum ConvType { T_CONV3 = 0, T_SKIP1 = 1, T_DOWN = 2, T_UP = 3 };
-enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_PAIR_256_512_1, I_PAIR_128_128_2, I_PAIR_256_256_1, I_COUNT };
+enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_PAIR_256_512_1, I_PAIR_128_128_2, I_PAIR_256_256_1, I_PAIR_128_256_1, I_COUNT };
 struct InstInfo { int nrs, dc, tm; bool fin; bool pair = false; bool acc3 = false; };
 const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32, 16, 2, true},
                                  {128, 64, 2, false},  {64, 64, 2, false},   {256, 128, 1, false},
                                  {128, 256, 2, false, false, true}, {256, 512, 1, false, false, true},
                                  // CTA-pair instances: nrs = rows of both CTAs = 2 x 1.5 x Cout
                                  {192, 256, 2, false, true, true}, {384, 512, 1, false, true, true},
-                                 {192, 128, 2, false, true}, {384, 256, 1, false, true}};
+                                 {192, 128, 2, false, true}, {384, 256, 1, false, true},
+                                 // one tile per CTA, two accumulator stages: the acc3 epilogue overlaps the next item
+                                 {192, 256, 1, false, true, true}};
 
 // activation tensors of the net
 enum ActId {
@@ -100,6 +102,8 @@ struct nbe_ctx {
   float eps = 1e-8f;
   int precision = NBE_PREC_SPLIT;
   bool pair = true;         // CTA pairs (cta_group::2) for the 3^3 velocity launches (NBE_PAIR=0 disables)
+  bool dbuf = false;        // 64-output acc3 pair launches: one tile per CTA + double-buffered TMEM (NBE_DBUF=0: two tiles)
+  int band_h = 2;           // tile rows per h-band of the item order (NBE_BAND; 0: whole planes)
   bool wide = true;         // w-halo'd activation blocks serving 9 taps per load (NBE_WIDE=0 disables)
   std::vector<Layer> layers;
   std::map<std::string, int> lidx;
@@ -235,7 +239,7 @@ int build_static(nbe_ctx* ctx) {
       bool ok = ctx->wide && vel;
       for (auto& p : s.parts) ok = ok && (p.type == T_CONV3 || p.type == T_SKIP1);
       if (!ok) continue;
-      if (s.inst == I_128_256_2) s.inst = I_PAIR_128_256_2;
+      if (s.inst == I_128_256_2) s.inst = ctx->dbuf ? I_PAIR_128_256_1 : I_PAIR_128_256_2;
       else if (s.inst == I_256_512_1) s.inst = I_PAIR_256_512_1;
       else if (s.inst == I_128_128_2) s.inst = I_PAIR_128_128_2;
       else if (s.inst == I_256_256_1) s.inst = I_PAIR_256_256_1;
@@ -628,6 +632,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           G.dd = static_cast<int8_t>(sc.crop + p.off + dd_);
           G.brow0 = tile0 * ii.nrs; G.brow_step = ii.nrs;
           G.pitch = static_cast<int8_t>(ntaps == 9 ? 10 : 8);
+          G.tps = static_cast<int8_t>((k16 && ntaps == 3) ? 3 : 1);
           cur_box_w = G.pitch;
           cur_kind = k16 ? 0 : kind;
           fill_ops(G, kind, sc, par, kd);
@@ -683,6 +688,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
         Lc.n_par = 1; Lc.out_w = OB.w; Lc.out_h = OB.h; Lc.out_d = OB.d;
         Lc.out_sw = C; Lc.out_sh = C * OB.w; Lc.out_sd = C * OB.w * OB.h;
       }
+      Lc.band_h = ctx->band_h;
       const long long tiles = 1ll * Lc.n_par * Lc.out_d * ((Lc.out_h + 16 * ii.tm - 1) / (16 * ii.tm)) * ((Lc.out_w + 7) / 8);
       H.grid = static_cast<int>(std::min<long long>(tiles, ctx->num_sms));
       if (ii.pair) H.grid = 2 * static_cast<int>(std::min<long long>((tiles + 1) / 2, ctx->num_sms / 2));
@@ -748,6 +754,7 @@ cudaError_t launch_conv(int inst, const ConvLaunch* dl, const GroupTable& gt, co
     case I_PAIR_256_512_1: return launch_pair<384, 512, 1>(dl, gt, fa, grid, st);
     case I_PAIR_128_128_2: return launch_pair<192, 128, 2>(dl, gt, fa, grid, st);
     case I_PAIR_256_256_1: return launch_pair<384, 256, 1>(dl, gt, fa, grid, st);
+    case I_PAIR_128_256_1: return launch_pair<192, 256, 1>(dl, gt, fa, grid, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -905,6 +912,8 @@ int nbe_create(nbe_ctx** out, int device) {
   ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
   if (const char* e = getenv("NBE_WIDE")) ctx->wide = atoi(e) != 0;
   if (const char* e = getenv("NBE_PAIR")) ctx->pair = atoi(e) != 0;
+  if (const char* e = getenv("NBE_DBUF")) ctx->dbuf = atoi(e) != 0;
+  if (const char* e = getenv("NBE_BAND")) ctx->band_h = atoi(e);
   cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   *out = ctx;
