@@ -120,6 +120,24 @@ int nbe_process_box_dev(nbe_ctx* ctx, const void* box_dev, int in_dtype, const i
 int nbe_host_register(nbe_ctx* ctx, void* ptr, size_t bytes);
 int nbe_host_unregister(nbe_ctx* ctx, void* ptr);
 
+/* ---- the step after the path: displacement -> density contrast -> P(k) shells ----
+ * Replaces the reference's third-party calls dj.get_delta_from_psi(psi, method="pm", res, worder,
+ * deconvolve) (scripts/core.py:396-409, 446-458) and PKL.Pk(delta, boxsize, MAS=...)
+ * (scripts/utils.py:1083-1090).  The FFT between the calls is the caller's (cuFFT): delta_k is the
+ * half-complex cube (res, res, res/2+1) of float2, unnormalised.
+ *
+ * nbe_density_from_psi: particles of the (n0,n1,n2) lattice displaced by psi_dev (3,n0,n1,n2) fp32,
+ * in the units of boxsize, are assigned to a periodic res^3 mesh with the B-spline of order worder
+ * (1 NGP, 2 CIC, 3 TSC, 4 PCS); delta_dev (res^3 fp32) receives rho/mean(rho) - 1.
+ * nbe_mas_deconvolve: delta_k /= prod_i sinc(pi k_i/res)^worder, in place.
+ * nbe_pk_bins: out_dev[3][nbins] (double; zeroed here) = shell sums of |delta_k / W^mas_order|^2,
+ * of |k|/k_F and of the mode count over the independent modes, shell = floor(|k|/k_F).           */
+int nbe_density_from_psi(nbe_ctx* ctx, const float* psi_dev, const int32_t n[3], float boxsize, int32_t res,
+                         int32_t worder, float* delta_dev, void* stream);
+int nbe_mas_deconvolve(nbe_ctx* ctx, void* delta_k_dev, int32_t res, int32_t worder, void* stream);
+int nbe_pk_bins(nbe_ctx* ctx, const void* delta_k_dev, int32_t res, int32_t mas_order, int32_t nbins,
+                double* out_dev, void* stream);
+
 /* Bytes of device memory the context needs for one (n0,n1,n2) sample (activation arena). */
 size_t nbe_workspace_bytes(nbe_ctx* ctx, const int32_t dims[3]);
 

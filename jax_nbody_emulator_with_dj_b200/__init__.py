@@ -9,6 +9,7 @@ from .subbox import SubboxConfig, SubboxProcessor
 from .cosmology import growth_factor, hubble_rate, growth_rate, dlogH_dloga, vel_norm, acc_norm
 from .models import (StyleNBodyEmulatorCore, StyleNBodyEmulatorVelCore, NBodyEmulatorCore,
                      NBodyEmulatorVelCore, init_params)
+from .density import get_delta_from_psi, deconvolve_mas_kernel, power_spectrum, mas_name_from_worder
 from ._lib import NBEError
 
 __version__ = "0.1.0"
@@ -18,4 +19,5 @@ __all__ = [
     "modulate_emulator_parameters", "modulate_emulator_parameters_vel",
     "growth_factor", "hubble_rate", "growth_rate", "dlogH_dloga", "vel_norm", "acc_norm",
     "StyleNBodyEmulatorCore", "StyleNBodyEmulatorVelCore", "NBodyEmulatorCore", "NBodyEmulatorVelCore",
+    "get_delta_from_psi", "deconvolve_mas_kernel", "power_spectrum", "mas_name_from_worder",
 ]

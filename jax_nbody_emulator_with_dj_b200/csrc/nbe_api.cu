@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "aux_kernels.cuh"
+#include "density.cuh"
 #include "conv_mma.cuh"
 
 using namespace nbe;
@@ -1259,6 +1260,61 @@ int nbe_host_unregister(nbe_ctx* ctx, void* ptr) {
   cudaError_t e = cudaHostUnregister(ptr);
   cudaGetLastError();
   return e == cudaSuccess ? NBE_OK : NBE_ERR_CUDA;
+}
+
+int nbe_density_from_psi(nbe_ctx* ctx, const float* psi_dev, const int32_t n[3], float boxsize, int32_t res,
+                         int32_t worder, float* delta_dev, void* stream) {
+  if (!ctx) return NBE_ERR_ARG;
+  if (!psi_dev || !delta_dev || !n || n[0] < 1 || n[1] < 1 || n[2] < 1 || res < 1 || !(boxsize > 0.f))
+    return fail(ctx, NBE_ERR_ARG, "nbe_density_from_psi: bad argument");
+  if (worder < 1 || worder > 4) return fail(ctx, NBE_ERR_ARG, "Unsupported mass-assignment order: %d", worder);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long cells = 1ll * res * res * res, np = 1ll * n[0] * n[1] * n[2];
+  CK(cudaMemsetAsync(delta_dev, 0, cells * sizeof(float), st));
+  const int grid = static_cast<int>(std::min<long long>((np + 255) / 256, 32ll * ctx->num_sms));
+  const float scale = static_cast<float>(res) / boxsize;
+  switch (worder) {
+    case 1: paint_kernel<1><<<grid, 256, 0, st>>>(psi_dev, n[0], n[1], n[2], res, scale, delta_dev); break;
+    case 2: paint_kernel<2><<<grid, 256, 0, st>>>(psi_dev, n[0], n[1], n[2], res, scale, delta_dev); break;
+    case 3: paint_kernel<3><<<grid, 256, 0, st>>>(psi_dev, n[0], n[1], n[2], res, scale, delta_dev); break;
+    default: paint_kernel<4><<<grid, 256, 0, st>>>(psi_dev, n[0], n[1], n[2], res, scale, delta_dev); break;
+  }
+  const int g2 = static_cast<int>(std::min<long long>((cells + 255) / 256, 32ll * ctx->num_sms));
+  rho_to_delta_kernel<<<g2, 256, 0, st>>>(delta_dev, cells, static_cast<float>(static_cast<double>(cells) / np));
+  ctx->launches += 2;
+  CK(cudaGetLastError());
+  return NBE_OK;
+}
+
+int nbe_mas_deconvolve(nbe_ctx* ctx, void* delta_k_dev, int32_t res, int32_t worder, void* stream) {
+  if (!ctx) return NBE_ERR_ARG;
+  if (!delta_k_dev || res < 1 || worder < 1 || worder > 4) return fail(ctx, NBE_ERR_ARG, "nbe_mas_deconvolve: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  const long long n = 1ll * res * res * (res / 2 + 1);
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 32ll * ctx->num_sms));
+  mas_deconvolve_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<float2*>(delta_k_dev), res, worder);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  return NBE_OK;
+}
+
+int nbe_pk_bins(nbe_ctx* ctx, const void* delta_k_dev, int32_t res, int32_t mas_order, int32_t nbins,
+                double* out_dev, void* stream) {
+  if (!ctx) return NBE_ERR_ARG;
+  if (!delta_k_dev || !out_dev || res < 1 || mas_order < 0 || mas_order > 4 || nbins < 1 || nbins > kPkMaxBins)
+    return fail(ctx, NBE_ERR_ARG, "nbe_pk_bins: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CK(cudaMemsetAsync(out_dev, 0, 3 * sizeof(double) * nbins, st));
+  const long long n = 1ll * res * res * (res / 2 + 1);
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 4ll * ctx->num_sms));
+  const size_t smem = 3 * sizeof(double) * nbins;
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(pk_bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  pk_bins_kernel<<<grid, 256, smem, st>>>(static_cast<const float2*>(delta_k_dev), res, mas_order, nbins, out_dev);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  return NBE_OK;
 }
 
 int64_t nbe_launch_count(nbe_ctx* ctx, int reset) {
