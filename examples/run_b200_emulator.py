@@ -96,6 +96,11 @@ def parser():
     ap.add_argument("--quiet", "-q", action="store_true")
     ap.add_argument("--params", type=Path, default=None, help=".npz with the pickled parameter tree under 'params'")
     ap.add_argument("--random-weights", type=int, default=None, metavar="SEED")
+    ap.add_argument("--boxsize", type=float, default=None,
+                    help="box side in the units of the displacement: also write emu_delta.npy (density contrast of "
+                         "q + emu_dis) and emu_pk.txt (k, P(k), Nmodes; MAS-corrected), the step scripts/core.py:446-458 "
+                         "runs after the emulator")
+    ap.add_argument("--mas-worder", type=int, default=2, choices=(2, 3, 4), help="mass assignment: 2 CIC, 3 TSC, 4 PCS")
     return ap
 
 
@@ -140,6 +145,14 @@ def main(argv=None):
             np.save(out / "emu_vel.npy", res[1])
         else:
             np.save(out / "emu_dis.npy", res)
+        if args.boxsize is not None:
+            if len(set(shape[1:])) != 1:
+                sys.exit(f"--boxsize needs a cubic box, got {shape[1:]}")
+            psi = np.asarray(res[0] if args.vel else res, dtype=np.float32)
+            delta = nb.get_delta_from_psi(psi, args.boxsize, worder=args.mas_worder)
+            pk = nb.power_spectrum(delta, args.boxsize, MAS=nb.mas_name_from_worder(args.mas_worder))
+            np.save(out / "emu_delta.npy", delta)
+            np.savetxt(out / "emu_pk.txt", np.column_stack(pk), header="k  P(k)  Nmodes")
         print(f"[{i + 1}/{n}] z={z:.4f}, Om={Om:.4f}: {dt:.2f}s -> {out}")
     print("\nDone!")
 

@@ -138,6 +138,13 @@ int nbe_mas_deconvolve(nbe_ctx* ctx, void* delta_k_dev, int32_t res, int32_t wor
 int nbe_pk_bins(nbe_ctx* ctx, const void* delta_k_dev, int32_t res, int32_t mas_order, int32_t nbins,
                 double* out_dev, void* stream);
 
+/* ---- the step before the path: linear density -> Zel'dovich displacement ----
+ * Replaces dj.with_lpt(n_order=1) + dj.evaluate_lpt_psi_at_a (scripts/core.py:396-397).
+ * psi_k_dev receives three half-complex cubes psi_j(k) = i k_j / k^2 * delta(k) (k = 0 and the
+ * Nyquist component of each derivative zeroed); the caller's inverse FFTs give psi in the units
+ * of boxsize when delta_k is the unnormalised forward FFT and the inverse is normalised.       */
+int nbe_za_psi_k(nbe_ctx* ctx, const void* delta_k_dev, int32_t res, float boxsize, void* psi_k_dev, void* stream);
+
 /* Bytes of device memory the context needs for one (n0,n1,n2) sample (activation arena). */
 size_t nbe_workspace_bytes(nbe_ctx* ctx, const int32_t dims[3]);
 

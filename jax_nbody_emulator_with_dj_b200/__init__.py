@@ -9,7 +9,8 @@ from .subbox import SubboxConfig, SubboxProcessor
 from .cosmology import growth_factor, hubble_rate, growth_rate, dlogH_dloga, vel_norm, acc_norm
 from .models import (StyleNBodyEmulatorCore, StyleNBodyEmulatorVelCore, NBodyEmulatorCore,
                      NBodyEmulatorVelCore, init_params)
-from .density import get_delta_from_psi, deconvolve_mas_kernel, power_spectrum, mas_name_from_worder
+from .density import (get_delta_from_psi, deconvolve_mas_kernel, power_spectrum, mas_name_from_worder,
+                      za_displacement_from_delta)
 from ._lib import NBEError
 
 __version__ = "0.1.0"
@@ -20,4 +21,5 @@ __all__ = [
     "growth_factor", "hubble_rate", "growth_rate", "dlogH_dloga", "vel_norm", "acc_norm",
     "StyleNBodyEmulatorCore", "StyleNBodyEmulatorVelCore", "NBodyEmulatorCore", "NBodyEmulatorVelCore",
     "get_delta_from_psi", "deconvolve_mas_kernel", "power_spectrum", "mas_name_from_worder",
+    "za_displacement_from_delta",
 ]

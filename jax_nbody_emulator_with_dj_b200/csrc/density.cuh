@@ -141,4 +141,30 @@ __global__ void __launch_bounds__(256) pk_bins_kernel(const float2* __restrict__
     if (sh[i] != 0.0) atomicAdd(&out[i], sh[i]);
 }
 
+// 1LPT (Zel'dovich) displacement in k space: psi_j(k) = i k_j / k^2 * delta(k), k in units of
+// k_F = 2 pi / boxsize; the k = 0 mode and the Nyquist component of each derivative are zeroed so
+// that the inverse real FFT is exact (scripts/core.py:396-397: dj.with_lpt(n_order=1) +
+// evaluate_lpt_psi_at_a).  out: three half-complex cubes, back to back.
+__global__ void __launch_bounds__(256) za_psi_k_kernel(const float2* __restrict__ dk, int res, float inv_kf,
+                                                        float2* __restrict__ out) {
+  const int nz = res / 2 + 1, mid = res / 2;
+  const bool even = (res % 2) == 0;
+  const long long n = 1ll * res * res * nz;
+  for (long long t = blockIdx.x * 256ll + threadIdx.x; t < n; t += 256ll * gridDim.x) {
+    const int kz = static_cast<int>(t % nz);
+    int ky = static_cast<int>((t / nz) % res), kx = static_cast<int>(t / (1ll * nz * res));
+    if (kx > mid) kx -= res;
+    if (ky > mid) ky -= res;
+    const float k2 = static_cast<float>(kx * kx + ky * ky + kz * kz);
+    const float2 v = dk[t];
+    const float s = k2 > 0.f ? inv_kf / k2 : 0.f;
+    const int kk[3] = {(even && kx == mid) ? 0 : kx, (even && ky == mid) ? 0 : ky, (even && kz == mid) ? 0 : kz};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float f = s * kk[j];
+      out[j * n + t] = make_float2(-f * v.y, f * v.x);       // i * f * (x + i y)
+    }
+  }
+}
+
 }  // namespace nbe

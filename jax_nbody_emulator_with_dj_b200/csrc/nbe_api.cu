@@ -1317,6 +1317,19 @@ int nbe_pk_bins(nbe_ctx* ctx, const void* delta_k_dev, int32_t res, int32_t mas_
   return NBE_OK;
 }
 
+int nbe_za_psi_k(nbe_ctx* ctx, const void* delta_k_dev, int32_t res, float boxsize, void* psi_k_dev, void* stream) {
+  if (!ctx) return NBE_ERR_ARG;
+  if (!delta_k_dev || !psi_k_dev || res < 1 || !(boxsize > 0.f)) return fail(ctx, NBE_ERR_ARG, "nbe_za_psi_k: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  const long long n = 1ll * res * res * (res / 2 + 1);
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 32ll * ctx->num_sms));
+  za_psi_k_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float2*>(delta_k_dev), res, boxsize / 6.283185307179586f, static_cast<float2*>(psi_k_dev));
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  return NBE_OK;
+}
+
 int64_t nbe_launch_count(nbe_ctx* ctx, int reset) {
   if (!ctx) return -1;
   const int64_t n = ctx->launches;

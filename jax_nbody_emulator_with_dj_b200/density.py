@@ -102,3 +102,26 @@ def power_spectrum(delta, boxsize, MAS=None):
         k3d = k[sel] / n[sel] * (2 * np.pi / boxsize)
         pk = p[sel] / n[sel] * (boxsize / res ** 2) ** 3
     return PkResult(k3d, pk, n[sel])
+
+
+def za_displacement_from_delta(delta_linear, boxsize, as_numpy=None):
+    """First-order LPT (Zel'dovich) displacement of a linear density field: div(psi) = -delta.
+
+    The step before the emulator (``scripts/core.py:396-397``: ``dj.with_lpt(n_order=1)`` +
+    ``evaluate_lpt_psi_at_a``; the growth factor is already in ``delta_linear`` when it is given at
+    the target epoch).  Returns psi (3, n, n, n) fp32 in the units of ``boxsize`` — the emulator's
+    input layout."""
+    torch = _torch()
+    eng = Engine.get()
+    if as_numpy is None:
+        as_numpy = not isinstance(delta_linear, torch.Tensor)
+    d = _dev(delta_linear, torch, torch.float32)
+    if d.ndim != 3 or len(set(d.shape)) != 1:
+        raise ValueError(f"`delta_linear` must be cubic 3D, got shape={tuple(d.shape)}")
+    res = d.shape[0]
+    dk = torch.fft.rfftn(d).contiguous()
+    pk = torch.empty((3,) + tuple(dk.shape), device="cuda", dtype=torch.complex64)
+    st = torch.cuda.current_stream().cuda_stream
+    eng._ck(eng.lib.nbe_za_psi_k(eng.h, dk.data_ptr(), res, float(boxsize), pk.data_ptr(), st))
+    psi = torch.fft.irfftn(pk, s=d.shape, dim=(1, 2, 3)).contiguous()
+    return psi.cpu().numpy() if as_numpy else psi

@@ -118,3 +118,24 @@ def power_spectrum(delta, boxsize, MAS=None):
         k3d = ks[sel] / nm[sel] * kf
         Pk = pk[sel] / nm[sel] * (boxsize / res ** 2) ** 3
     return k3d, Pk, nm[sel]
+
+
+def za_displacement(delta, boxsize):
+    """psi (3, n, n, n) with psi_k = i k / k^2 delta_k (scripts/core.py:396-397, DISCO-DJ 1LPT);
+    k = 0 and the Nyquist component of each derivative zeroed."""
+    delta = np.asarray(delta, np.float64)
+    res = delta.shape[0]
+    mid = res // 2
+    kf = 2 * np.pi / boxsize
+    k1 = np.fft.fftfreq(res, 1.0 / res)
+    kz = np.arange(res // 2 + 1, dtype=np.float64)
+    KX, KY, KZ = np.meshgrid(k1, k1, kz, indexing="ij")
+    k2 = KX ** 2 + KY ** 2 + KZ ** 2
+    dk = np.fft.rfftn(delta)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        s = np.where(k2 > 0, 1.0 / (kf * k2), 0.0)
+    out = []
+    for K in (KX, KY, KZ):
+        Kd = np.where((np.abs(K) == mid) & (res % 2 == 0), 0.0, K)
+        out.append(np.fft.irfftn(1j * s * Kd * dk, s=delta.shape, axes=(0, 1, 2)))
+    return np.stack(out)

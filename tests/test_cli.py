@@ -55,3 +55,23 @@ def test_end_to_end_files(tmp_path, golden_dir):
               "--output_dirs", str(d), "--ndiv", "1,1,2", "--random-weights", "42", "--no-vel", "--no-style", "-q"])
     dis16 = np.load(d / "emu_dis.npy")
     assert dis16.dtype == np.float16 and rel_l2(dis16, g["disp"]) <= 2e-3
+
+
+@pytest.mark.gpu
+def test_density_and_power_spectrum_outputs(tmp_path):
+    """--boxsize: emu_delta.npy / emu_pk.txt, the step the reference driver runs after the emulator
+    (scripts/core.py:446-458), checked against the numpy oracle on the CLI's own displacement."""
+    from oracle import density as D
+    d = _sim(tmp_path, size=(16, 16, 16), seed=5)
+    cli.main(["--cosmo_param_files", str(d / "params.npy"), "--displacement_files", str(d / "dis.npy"),
+              "--output_dirs", str(d), "--ndiv", "1,1,1", "--random-weights", "42", "--output-precision", "f32",
+              "--no-vel", "--boxsize", "16", "--mas-worder", "3", "-q"])
+    dis, delta, pk = np.load(d / "emu_dis.npy"), np.load(d / "emu_delta.npy"), np.loadtxt(d / "emu_pk.txt")
+    ref = D.delta_from_psi(dis.astype(np.float64), 16.0, worder=3)
+    assert np.abs(delta - ref).max() / np.sqrt(np.mean((1 + ref) ** 2)) < 2e-5
+    k, P, N = D.power_spectrum(ref, 16.0, MAS="TSC")
+    assert np.array_equal(pk[:, 2], N) and np.allclose(pk[:, 1], P, rtol=1e-3) and np.allclose(pk[:, 0], k, rtol=1e-6)
+    with pytest.raises(SystemExit):
+        d2 = _sim(tmp_path / "x", size=(8, 8, 16)) if (tmp_path / "x").mkdir() is None else None
+        cli.main(["--cosmo_param_files", str(d2 / "params.npy"), "--displacement_files", str(d2 / "dis.npy"),
+                  "--output_dirs", str(d2), "--ndiv", "1,1,2", "--random-weights", "42", "--boxsize", "8", "-q"])

@@ -86,3 +86,15 @@ def test_large_mesh_mass_conservation_and_shift():
     assert abs(float(a.double().mean())) < 1e-6
     b = nb.get_delta_from_psi(psi + 2.0, 256.0, worder=2)          # two cells along every axis
     assert float((torch.roll(a, (2, 2, 2), (0, 1, 2)) - b).abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("res", [15, 16, 48])
+def test_zeldovich_displacement_matches_oracle(res):
+    d = np.random.default_rng(res).standard_normal((res, res, res)).astype(np.float32)
+    got = nb.za_displacement_from_delta(d, 75.0)
+    ref = D.za_displacement(d.astype(np.float64), 75.0)
+    assert got.shape == (3, res, res, res) and got.dtype == np.float32
+    assert np.sqrt(np.mean((got - ref) ** 2) / np.mean(ref ** 2)) < 1e-5      # fp32 cuFFT vs fp64 numpy
+    # the emulator takes it as is: (3, n, n, n), units of the box
+    t = nb.za_displacement_from_delta(torch.from_numpy(d).cuda(), 75.0)
+    assert t.is_cuda and t.is_contiguous() and np.abs(t.cpu().numpy() - got).max() < 1e-5

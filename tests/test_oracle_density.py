@@ -71,3 +71,21 @@ def test_deconvolution_inverts_the_window():
     k, P0, _ = D.power_spectrum(d, 30.0)
     _, P1, _ = D.power_spectrum(smooth, 30.0, MAS="CIC")
     assert np.allclose(P0, P1, rtol=1e-9)
+
+
+def test_zeldovich_plane_wave_and_divergence():
+    res, L = 16, 40.0
+    x = np.arange(res) * (L / res)
+    kk = 2 * np.pi * 2 / L
+    d = 0.2 * np.cos(kk * x)[None, :, None] * np.ones((res, 1, res))
+    psi = D.za_displacement(d, L)
+    assert np.allclose(psi[1], -0.2 / kk * np.sin(kk * x)[None, :, None] * np.ones((res, 1, res)), atol=1e-12)
+    assert np.abs(psi[0]).max() < 1e-12 and np.abs(psi[2]).max() < 1e-12
+    g = np.random.default_rng(0).standard_normal((12, 12, 12)); g -= g.mean()
+    psi = D.za_displacement(g, 12.0)
+    # spectral divergence of psi gives back -delta except on the zeroed Nyquist planes (none for these modes if we low-pass)
+    gk = np.fft.rfftn(g); k1 = np.fft.fftfreq(12, 1 / 12.0); kz = np.arange(7.0)
+    KX, KY, KZ = np.meshgrid(k1, k1, kz, indexing="ij")
+    low = (np.abs(KX) < 6) & (np.abs(KY) < 6) & (KZ < 6)
+    div = sum(1j * (2 * np.pi / 12.0) * K * np.fft.rfftn(psi[i]) for i, K in enumerate((KX, KY, KZ)))
+    assert np.allclose(div[low], -gk[low], atol=1e-9)
