@@ -248,6 +248,23 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     h0 = th * 16 * TM;
   };
 
+  // With two h-stacked tiles per item, the upper tile of the last tile row can lie wholly outside
+  // the output (e.g. out_h = 130: rows 144..159).  Its MMAs are skipped (the barrier protocol is
+  // kept), which saves the tensor work and, the board being power-limited, its energy.  In a pair
+  // the M = 256 instruction covers both CTAs' items, so the tile must be dead in both.
+  auto tile_dead = [&](long long it0, int t) -> bool {
+    if (TM != 2 || t == 0) return false;
+    bool dead = true;
+    for (int c = 0; c < (PAIR ? 2 : 1); ++c) {
+      const long long item = it0 + c;
+      if (item >= n_items) continue;
+      int par, w0, h0, d0;
+      decode(item, par, w0, h0, d0);
+      dead = dead && (h0 + 16 * t >= out_h);
+    }
+    return dead;
+  };
+
   if (warp == 0) {
     // ------------------------------------------------ A producer (activation blocks)
     if (lane == 0) {
@@ -320,6 +337,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     for (long long item = item_first; item < n_items && (!PAIR || rank == 0); item += gridDim.x) {
       mbar_wait(&acc_empty[buf], pacc ^ 1);
       tc_fence_after();
+      const bool dead = tile_dead(item, my_tile);
       for (int g = 0; g < n_groups; ++g) {
         const GroupDesc& G = gt.g[g];
         const int ntaps = G.ntaps, n_ops = G.n_ops;
@@ -355,7 +373,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
           if (elect_one()) {
 #pragma unroll
             for (int t = 0; t < TM; ++t) {
-              if (kIssuers == 2 && t != my_tile) continue;
+              if ((kIssuers == 2 && t != my_tile) || dead) continue;
               const uint32_t d_tile = tmem_u + (buf * TM + t) * DC;
               const uint32_t kw = ntaps == 9 ? static_cast<uint32_t>(j) / 3u : 0u;
               const uint32_t kh = ntaps == 9 ? static_cast<uint32_t>(j) % 3u : static_cast<uint32_t>(j);
@@ -425,9 +443,10 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
       decode(item_ok ? item : 0, par, w0, h0, d0);
       mbar_wait(&acc_full[buf], pacc);
       tc_fence_after();
+      const bool dead = tile_dead(it0, eg);       // nothing was accumulated: the columns are still zero
 #pragma unroll
       for (int t = 0; t < TM; ++t) {
-        if (TM == 2 && t != eg) continue;
+        if ((TM == 2 && t != eg) || dead) continue;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (buf * TM + t) * DC;
         const int w = w0 + (r & 7);
         const int h = h0 + t * 16 + (r >> 3);
