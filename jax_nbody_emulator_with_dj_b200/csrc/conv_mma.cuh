@@ -142,6 +142,7 @@ struct ConvCfg {
                                    : kColsRaw <= 256 ? 256 : 512;
   static constexpr int kSmemBytes = 1024 + kNA * kAStage + kNB * kBStage + kCtrl;
   static_assert(kNB >= 2, "not enough shared memory for the B ring");
+  static_assert(3 * kBRows * 32 <= kBStage, "a weight stage holds three 16-channel taps");
   static_assert(kColsRaw <= 512, "TMEM overflow");
 };
 
@@ -307,11 +308,18 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
           const int tps = G.tps;
           for (int j = 0; j < G.ntaps; j += tps) {
             mbar_wait(&b_empty[s], ph ^ 1);
-            if (!PAIR || rank == 0) mbar_expect_tx(&b_full[s], bytes * tps * (PAIR ? 2 : 1));
-            for (int t = 0; t < tps; ++t) {
-              uint8_t* dst = b_smem + s * Cfg::kBStage + t * bytes;
-              if constexpr (PAIR) tma_load_2d_2sm(dst, bm, &b_full[s], 0, row0 + (j + t) * G.brow_step);
-              else tma_load_2d(dst, bm, &b_full[s], 0, row0 + (j + t) * G.brow_step);
+            uint8_t* dst = b_smem + s * Cfg::kBStage;
+            if (G.kc16) {
+              // 16-channel tiles: one 3-D box {16 ch, this CTA's rows, 3 consecutive taps} per stage
+              if (!PAIR || rank == 0) mbar_expect_tx(&b_full[s], bytes * 3 * (PAIR ? 2 : 1));
+              const int tile = (G.brow0 + par * par_brow_step) / NRS + j;
+              const int r0 = PAIR ? static_cast<int>(rank) * Cfg::kBRows : 0;
+              if constexpr (PAIR) tma_load_3d_2sm(dst, bm, &b_full[s], 0, r0, tile);
+              else tma_load_3d(dst, bm, &b_full[s], 0, r0, tile);
+            } else {
+              if (!PAIR || rank == 0) mbar_expect_tx(&b_full[s], bytes * (PAIR ? 2 : 1));
+              if constexpr (PAIR) tma_load_2d_2sm(dst, bm, &b_full[s], 0, row0 + j * G.brow_step);
+              else tma_load_2d(dst, bm, &b_full[s], 0, row0 + j * G.brow_step);
             }
             if (++s == Cfg::kNB) { s = 0; ph ^= 1; }
           }
@@ -363,6 +371,37 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
         const uint32_t a_lo = ((smem_u32(a_smem + sa * Cfg::kAStage) & 0x3FFFFu) >> 4) | (1u << 16);
         const int tps = G.tps;
         const uint32_t tap16 = static_cast<uint32_t>(Cfg::kBRows) * row16;   // one tap's tile in 16-byte units
+        if (k16 && tps == 3) {
+          // 16-channel rows: one MMA per tap, so the per-tap wait / elect / commit round trip (about 400
+          // cycles of dependent uniform instructions) was the limiter of the first layer; issue the three
+          // taps of a stage from one elected section
+          for (int j = 0; j < ntaps; j += 3) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint32_t b_base = ((smem_u32(b_smem + sb * Cfg::kBStage) & 0x3FFFFu) >> 4) | (1u << 16);
+            if (elect_one()) {
+              if (!dead) {
+                const uint32_t d_tile = tmem_u + (buf * TM + my_tile) * DC;
+#pragma unroll
+                for (int jt = 0; jt < 3; ++jt) {
+                  const uint32_t jj = static_cast<uint32_t>(j + jt);
+                  const uint32_t kw = ntaps == 9 ? jj / 3u : 0u;
+                  const uint32_t kh = ntaps == 9 ? jj % 3u : jj;
+                  const uint32_t a_row = (static_cast<uint32_t>(my_tile * 16) + kh) * sbo16 + kw * row16;
+                  const uint32_t a_hi = desc_hi | (kBaseOffsetMode ? (((a_lo + a_row) >> 3) & 7u) << 17 : 0u);
+#pragma unroll
+                  for (int o = 0; o < 3; ++o)
+                    if (o < n_ops)
+                      mma(d_tile + op_d[o], (static_cast<uint64_t>(a_hi) << 32) | (a_lo + op_a[o] + a_row),
+                          (static_cast<uint64_t>(bdesc_hi) << 32) | (b_base + jt * tap16 + op_b[o]), op_i[o], 1u);
+                }
+              }
+              commit(&b_empty[sb]);
+            }
+            __syncwarp();
+            if (++sb == Cfg::kNB) { sb = 0; pb ^= 1; }
+          }
+        } else
         for (int j = 0, jt = 0; j < ntaps; ++j) {
           if (jt == 0) {
             mbar_wait(&b_full[sb], pb);

@@ -105,6 +105,7 @@ struct nbe_ctx {
   bool pair = true;         // CTA pairs (cta_group::2) for the 3^3 velocity launches (NBE_PAIR=0 disables)
   bool dbuf = false;        // 64-output acc3 pair launches: one tile per CTA + double-buffered TMEM (NBE_DBUF=0: two tiles)
   int band_h = 2;           // tile rows per h-band of the item order (NBE_BAND; 0: whole planes)
+  bool wide16 = true;       // also for the 16-channel first layer (32-byte rows, SWIZZLE_32B row shifts; NBE_WIDE16)
   bool wide = true;         // w-halo'd activation blocks serving 9 taps per load (NBE_WIDE=0 disables)
   std::vector<Layer> layers;
   std::map<std::string, int> lidx;
@@ -408,6 +409,20 @@ int make_b_map(nbe_ctx* ctx, CUtensorMap* m, const __half* base, int kc, long lo
   return NBE_OK;
 }
 
+// 16-channel weight tiles as {16 ch, nrs rows, tiles}: one box = this CTA's rows of three consecutive taps
+int make_b_map16(nbe_ctx* ctx, CUtensorMap* m, const __half* base, int n_tiles, int nrs, int box_rows) {
+  if (n_tiles <= 0) { memset(m, 0, sizeof(*m)); return NBE_OK; }
+  cuuint64_t dims[3] = {16, static_cast<cuuint64_t>(nrs), static_cast<cuuint64_t>(n_tiles)};
+  cuuint64_t str[2] = {32, static_cast<cuuint64_t>(nrs) * 32};
+  cuuint32_t box[3] = {16, static_cast<cuuint32_t>(box_rows), 3};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, str, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, NBE_ERR_CUDA, "cuTensorMapEncodeTiled(B16 tiles=%d) -> %d", n_tiles, (int)r);
+  return NBE_OK;
+}
+
 // ----------------------------------------------------------------------------------------
 // per-shape plan
 // ----------------------------------------------------------------------------------------
@@ -498,7 +513,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
       };
       const int box_rows = ii.pair ? ii.nrs / 2 : ii.nrs;
       if ((rc = make_b_map(ctx, &Lc.bmap64, packed + s.b64_off, 64, static_cast<long long>(s.n_tiles64) * ii.nrs, box_rows)) ||
-          (rc = make_b_map(ctx, &Lc.bmap16, packed + s.b16_off, 16, static_cast<long long>(s.n_tiles16) * ii.nrs, box_rows))) { delete P; return rc; }
+          (rc = make_b_map16(ctx, &Lc.bmap16, packed + s.b16_off, s.n_tiles16, ii.nrs, box_rows))) { delete P; return rc; }
 
       int ng = 0;
       bool bad = false;
@@ -633,7 +648,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           G.dd = static_cast<int8_t>(sc.crop + p.off + dd_);
           G.brow0 = tile0 * ii.nrs; G.brow_step = ii.nrs;
           G.pitch = static_cast<int8_t>(ntaps == 9 ? 10 : 8);
-          G.tps = static_cast<int8_t>((k16 && ntaps == 3) ? 3 : 1);
+          G.tps = static_cast<int8_t>((k16 && ntaps >= 3) ? 3 : 1);
           cur_box_w = G.pitch;
           cur_kind = k16 ? 0 : kind;
           fill_ops(G, kind, sc, par, kd);
@@ -643,7 +658,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
         const double m = vel ? ((k16 || false) ? 2.0 : 3.0) : 1.0;
         double vout = static_cast<double>(OB.d) * OB.h * OB.w;
         if (p.type == T_CONV3) {
-          const bool wide = ctx->wide && !k16;
+          const bool wide = ctx->wide && (!k16 || ctx->wide16);
           for (int kd = 0; kd < 3; ++kd)
             for (int q = 0; q < nkc; ++q) for (int kind = 0; kind < nk; ++kind) {
               const int t0 = tb + ((kd * nkc + q) * nk + kind) * 9;
@@ -914,6 +929,7 @@ int nbe_create(nbe_ctx** out, int device) {
   if (const char* e = getenv("NBE_WIDE")) ctx->wide = atoi(e) != 0;
   if (const char* e = getenv("NBE_PAIR")) ctx->pair = atoi(e) != 0;
   if (const char* e = getenv("NBE_DBUF")) ctx->dbuf = atoi(e) != 0;
+  if (const char* e = getenv("NBE_WIDE16")) ctx->wide16 = atoi(e) != 0;
   if (const char* e = getenv("NBE_BAND")) ctx->band_h = atoi(e);
   cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
