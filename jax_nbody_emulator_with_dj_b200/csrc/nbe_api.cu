@@ -1186,61 +1186,19 @@ int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32
   if ((rc = ensure(ctx, &ctx->d_box, &ctx->box_cap, in_bytes))) return rc;
   if ((rc = ensure(ctx, &ctx->d_disp, &ctx->out_cap, out_bytes))) return rc;
   if (ctx->vel && (rc = ensure(ctx, &ctx->d_velo, &ctx->velo_cap, out_bytes))) return rc;
-  // Upload in two phases so that compute starts before the whole slab has arrived: phase A (compute
-  // stream) brings the H-rows the first subbox reads, for every plane of the slab; phase B (copy
-  // stream) the remaining rows, and the compute stream waits for it only before the first subbox
-  // with a different H window.  Planes are uploaded whole (single phase) when that window covers
-  // all rows or every subbox shares it.
-  std::vector<uint8_t> in_a(static_cast<size_t>(S1), 0);
-  for (int i = 0; i < plen[1]; ++i) in_a[tabs[plen[0] + i]] = 1;
-  int n_cover = 1;                                          // subboxes [0, n_cover) read only phase-A rows
-  for (; n_cover < sub_count; ++n_cover) {
-    bool same = true;
-    for (int i = 0; i < plen[1] && same; ++i) same = in_a[tabs[static_cast<size_t>(n_cover) * per + plen[0] + i]] != 0;
-    if (!same) break;
-  }
-  int64_t rows_a = 0;
-  for (int64_t h = 0; h < S1; ++h) rows_a += in_a[h];
-  const bool two_phase = n_cover < sub_count && rows_a < S1;
-  cudaEvent_t up_b = nullptr;
-  auto upload_rows = [&](int64_t h0, int64_t h1, cudaStream_t q) -> int {       // rows [h0, h1) of every slab plane
-    for (int64_t d0 = 0; d0 < S0;) {                      // runs of consecutive planes = consecutive slots
-      if (slot[d0] < 0) { ++d0; continue; }
-      int64_t d1 = d0;
-      while (d1 < S0 && slot[d1] >= 0) ++d1;
-      for (int c = 0; c < 3; ++c) {
-        uint8_t* dst = static_cast<uint8_t*>(ctx->d_box) + (static_cast<size_t>(c) * n_slots + slot[d0]) * plane_in;
-        const uint8_t* src = static_cast<const uint8_t*>(in_host) + (static_cast<size_t>(c) * S0 + d0) * plane_in;
-        if (h0 == 0 && h1 == S1) {
-          CK(cudaMemcpyAsync(dst, src, static_cast<size_t>(d1 - d0) * plane_in, cudaMemcpyHostToDevice, q));
-        } else {
-          cudaMemcpy3DParms p3 = {};
-          p3.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(src), S2 * ies, S2, S1);
-          p3.dstPtr = make_cudaPitchedPtr(dst, S2 * ies, S2, S1);
-          p3.srcPos = make_cudaPos(0, static_cast<size_t>(h0), 0);
-          p3.dstPos = p3.srcPos;
-          p3.extent = make_cudaExtent(static_cast<size_t>(S2) * ies, static_cast<size_t>(h1 - h0), static_cast<size_t>(d1 - d0));
-          p3.kind = cudaMemcpyHostToDevice;
-          CK(cudaMemcpy3DAsync(&p3, q));
-        }
-      }
-      d0 = d1;
-    }
-    return NBE_OK;
-  };
-  if (!two_phase) {
-    if ((rc = upload_rows(0, S1, st))) return rc;
-  } else {
-    for (int phase = 0; phase < 2; ++phase)
-      for (int64_t h0 = 0; h0 < S1;) {                    // runs of rows inside (phase 0) / outside (phase 1) the window
-        if ((in_a[h0] != 0) != (phase == 0)) { ++h0; continue; }
-        int64_t h1 = h0;
-        while (h1 < S1 && (in_a[h1] != 0) == (phase == 0)) ++h1;
-        if ((rc = upload_rows(h0, h1, phase == 0 ? st : cs))) return rc;
-        h0 = h1;
-      }
-    CK(cudaEventCreateWithFlags(&up_b, cudaEventDisableTiming));
-    CK(cudaEventRecord(up_b, cs));
+  // Whole planes, one copy per channel and run of consecutive planes, on the compute stream.
+  // (A split upload -- the first subbox's H-rows first, the rest on the copy stream -- saved ~8 ms
+  // per call but faulted with "illegal memory access" whenever the plan was rebuilt inside the same
+  // call; not understood, so not shipped.)
+  for (int64_t d0 = 0; d0 < S0;) {                        // runs of consecutive planes = consecutive slots
+    if (slot[d0] < 0) { ++d0; continue; }
+    int64_t d1 = d0;
+    while (d1 < S0 && slot[d1] >= 0) ++d1;
+    for (int c = 0; c < 3; ++c)
+      CK(cudaMemcpyAsync(static_cast<uint8_t*>(ctx->d_box) + (static_cast<size_t>(c) * n_slots + slot[d0]) * plane_in,
+                         static_cast<const uint8_t*>(in_host) + (static_cast<size_t>(c) * S0 + d0) * plane_in,
+                         static_cast<size_t>(d1 - d0) * plane_in, cudaMemcpyHostToDevice, st));
+    d0 = d1;
   }
   cudaEvent_t done;
   CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
@@ -1296,7 +1254,6 @@ int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32
   const int32_t size_out[3] = {static_cast<int32_t>(ND), size[1], size[2]};
   rc = process_box_core(ctx, ctx->d_box, in_dtype, size_in, size_out, crop, plen, tabs.data(), anchors.data(), 0, sub_count,
                         Dz, vel_fac, ctx->d_disp, ctx->d_velo, out_dtype, st, [&](int s) -> int {
-                          if (two_phase && s + 1 == n_cover) CK(cudaStreamWaitEvent(st, up_b, 0));   // next subbox reads phase-B rows
                           // full (H, W)-tiling runs go back as one contiguous copy per channel when they end;
                           // everything else -- partial runs (sharded ranges) and the last run, whose copy
                           // nothing would hide -- is pasted subbox by subbox behind the next subbox's compute
@@ -1305,7 +1262,6 @@ int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32
   cudaError_t e1 = cudaStreamSynchronize(st);      // also on error paths: the caller's buffers must be quiescent
   cudaError_t e2 = cudaStreamSynchronize(cs);
   cudaEventDestroy(done);
-  if (up_b) cudaEventDestroy(up_b);
   if (rc) return rc;
   if (e1 != cudaSuccess) return fail(ctx, NBE_ERR_CUDA, "process_box: %s", cudaGetErrorString(e1));
   if (e2 != cudaSuccess) return fail(ctx, NBE_ERR_CUDA, "process_box copy: %s", cudaGetErrorString(e2));
