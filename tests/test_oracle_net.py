@@ -156,3 +156,60 @@ def test_cosmology_oracle_known_values():   # README.md:178-180; tests/test_cosm
     h = 1e-5
     fd = -(np.log(oc.growth_factor(0.5 + h, 0.3)) - np.log(oc.growth_factor(0.5 - h, 0.3))) / (2 * h) * 1.5
     assert abs(fd - oc.growth_rate(0.5, 0.3)) < 1e-6
+
+
+def _literal_layer(lp, x, dx, s, kind):
+    """One Style layer restated with explicit index arithmetic (no torch conv): the formulas of
+    SURVEY App. B / style_layers_vel.py:62-147, 235-255, in float64."""
+    W = np.asarray(lp["weight"], np.float64); SW = np.asarray(lp["style_weight"], np.float64)
+    sb = np.asarray(lp["style_bias"], np.float64); b = np.asarray(lp["bias"], np.float64)
+    O, I, k = W.shape[0], W.shape[1], W.shape[2]
+    s_mod = SW @ s + sb                                             # (I,)
+    w = W * s_mod[None, :, None, None, None]
+    norm = np.sqrt((w ** 2).sum(axis=(1, 2, 3, 4), keepdims=True) + 1e-8)
+    wn = w / norm
+    dws = W * SW[:, 1][None, :, None, None, None]
+    dwn = dws / norm - w * (w * dws).sum(axis=(1, 2, 3, 4), keepdims=True) / norm ** 3
+    if dx is None:
+        dwn = dwn + wn / (s[1] + 1.0)
+
+    def corr(inp, wt):
+        n = inp.shape[1:]
+        if kind == "up":                                            # out[2i+a] = sum_ci w[o,ci,1-a,1-b,1-c] x[ci,i,j,k]
+            out = np.zeros((O,) + tuple(2 * m for m in n))
+            for a in range(2):
+                for bb in range(2):
+                    for c in range(2):
+                        out[:, a::2, bb::2, c::2] = np.einsum("oi,idhw->odhw", wt[:, :, 1 - a, 1 - bb, 1 - c], inp)
+            return out
+        st = 2 if kind == "down" else 1
+        m = tuple((d - k) // st + 1 for d in n)
+        out = np.zeros((O,) + m)
+        for a in range(k):
+            for bb in range(k):
+                for c in range(k):
+                    win = inp[:, a:a + st * (m[0] - 1) + 1:st, bb:bb + st * (m[1] - 1) + 1:st, c:c + st * (m[2] - 1) + 1:st]
+                    out += np.einsum("oi,idhw->odhw", wt[:, :, a, bb, c], win)
+        return out
+
+    y = corr(x, wn) + b[:, None, None, None]
+    dy = corr(x, dwn) + (corr(dx, wn) if dx is not None else 0.0)
+    return y, dy
+
+
+@pytest.mark.parametrize("kind,k", [("conv", 3), ("skip", 1), ("down", 2), ("up", 2)])
+@pytest.mark.parametrize("first", [True, False])
+def test_style_layer_matches_literal_restatement(kind, k, first):
+    rng = np.random.default_rng(k * 10 + first)
+    I, O, n = 3, 4, 6
+    lp = {"weight": rng.standard_normal((O, I, k, k, k)), "bias": rng.standard_normal(O),
+          "style_weight": rng.standard_normal((I, 2)), "style_bias": 1 + 0.1 * rng.standard_normal(I)}
+    x = rng.standard_normal((I, n, n, n)); dx = None if first else rng.standard_normal((I, n, n, n))
+    s = np.array([(0.31 - 0.3) * 5, 0.77 - 1.0])
+    net = Net(True, True, torch.float64)
+    y, dy = net.layer(lp, torch.from_numpy(x)[None], None if first else torch.from_numpy(dx)[None], torch.from_numpy(s)[None],
+                      k, stride=2 if kind == "down" else 1, up=kind == "up")
+    ry, rdy = _literal_layer(lp, x, dx, s, kind)
+    assert y.shape[1:] == ry.shape
+    assert np.allclose(y[0].numpy(), ry, rtol=1e-11, atol=1e-12)
+    assert np.allclose(dy[0].numpy(), rdy, rtol=1e-10, atol=1e-11)
