@@ -108,6 +108,29 @@ int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32
                     const int32_t* add_idx0, int sub_first, int sub_count, float Dz, float vel_fac,
                     void* disp_host, void* vel_host, int out_dtype);
 
+/* nbe_process_box over ALL GPUs of the process in one call (what the reference user's single
+ * processor.process_box(box, z, Om) call, subbox.py:139-219, becomes on an 8-GPU box): ctxs[0..ngpu) are
+ * contexts on distinct devices, each with the same parameters set and modulated.  The range
+ * [sub_first, sub_first+sub_count) is cut into ngpu contiguous shares (the first sub_count % ngpu
+ * contexts get one more subbox); one host thread per context uploads its (D, H) window from the SAME
+ * in_host and copies its finished blocks into the SAME disp_host / vel_host, which should be
+ * page-locked (nbe_host_register, or cudaHostAlloc'ed by the caller).  The shares are disjoint: no
+ * exchange step, no per-GPU copy of the box in host memory.  Synchronous; returns the first error
+ * (message on ctxs[0]).                                                                          */
+int nbe_process_box_multi(nbe_ctx** ctxs, int ngpu, const void* in_host, int in_dtype, const int32_t size[3],
+                          const int32_t crop[3], const int32_t plen[3], const int32_t* crop_idx,
+                          const int32_t* add_idx0, int sub_first, int sub_count, float Dz, float vel_fac,
+                          void* disp_host, void* vel_host, int out_dtype);
+
+/* nbe_process_box with the results left ON THE DEVICE in block layout: disp_blocks_dev / vel_blocks_dev
+ * are (sub_count, 3, crop0, crop1, crop2) of out_dtype, one contiguous record per subbox in index order.
+ * This is the send buffer of the optional output gather of a sharded box (one process per GPU):
+ * ncclAllGather of the records over NVLink, no host round trip (SubboxProcessor.process_box(gather=...)). */
+int nbe_process_box_blocks(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32_t size[3],
+                           const int32_t crop[3], const int32_t plen[3], const int32_t* crop_idx,
+                           const int32_t* add_idx0, int sub_first, int sub_count, float Dz, float vel_fac,
+                           void* disp_blocks_dev, void* vel_blocks_dev, int out_dtype);
+
 /* Same decomposition with the box and the outputs resident in device memory ((3,size) each);
  * asynchronous on `stream`, no host<->device traffic besides the index tables.            */
 int nbe_process_box_dev(nbe_ctx* ctx, const void* box_dev, int in_dtype, const int32_t size[3],

@@ -22,6 +22,7 @@ NBE_PREC_SPLIT, NBE_PREC_FP16 = 0, 1
 EXPORTS = (
     "nbe_create", "nbe_destroy", "nbe_last_error", "nbe_version", "nbe_set_params", "nbe_set_precision",
     "nbe_modulate", "nbe_get_modulated", "nbe_forward", "nbe_process_box", "nbe_process_box_dev",
+    "nbe_process_box_multi", "nbe_process_box_blocks",
     "nbe_workspace_bytes", "nbe_host_register", "nbe_host_unregister",
     "nbe_launch_count", "nbe_set_profiling", "nbe_get_profile", "nbe_debug_read_act",
     "nbe_density_from_psi", "nbe_mas_deconvolve", "nbe_pk_bins", "nbe_za_psi_k",
@@ -85,6 +86,9 @@ def load():
         lib.nbe_forward.argtypes = [vp, vp, C.c_int, C.c_int, i32p, f32p, f32p, vp, vp, C.c_int, vp]
         lib.nbe_process_box.argtypes = [vp, vp, C.c_int, i32p, i32p, i32p, i32p, i32p, C.c_int, C.c_int,
                                         C.c_float, C.c_float, vp, vp, C.c_int]
+        lib.nbe_process_box_multi.argtypes = [C.POINTER(vp), C.c_int, vp, C.c_int, i32p, i32p, i32p, i32p, i32p, C.c_int,
+                                              C.c_int, C.c_float, C.c_float, vp, vp, C.c_int]
+        lib.nbe_process_box_blocks.argtypes = lib.nbe_process_box.argtypes
         lib.nbe_process_box_dev.argtypes = [vp, vp, C.c_int, i32p, i32p, i32p, i32p, i32p, C.c_int, C.c_int,
                                             C.c_float, C.c_float, vp, vp, C.c_int, vp]
         lib.nbe_host_register.argtypes = [vp, vp, C.c_size_t]

@@ -48,7 +48,10 @@ struct GroupDesc {
   int8_t dw, dh, dd;  // block origin relative to the tile origin
   int8_t pitch;       // rows per h-line of the block: 8, or 10 (w-halo'd "wide" block, kw taps by row shift)
   int8_t tps;         // taps per weight stage: 1, or 3 for 16-channel rows (three small tiles share a stage)
-  int8_t pad_[3];
+  // early-drain protocol of the per-kd accumulator layout (EARLY instances, see the epilogue):
+  int8_t pre_wait;    // before this group's MMAs wait for  1: y0_empty  2: acc_empty (dy | y1 | y2)
+  int8_t post_sig;    // after this group commit           1: y0_full   2: y1_full
+  int8_t lo_stage;    // weight stages of this group use the short box of bmap64_lo (lo products)
   int32_t brow0;      // B row of tap 0
   int32_t brow_step;  // B rows between consecutive taps
   MmaOp ops[3];
@@ -66,6 +69,8 @@ struct alignas(128) ConvLaunch {
   CUtensorMap amap[kMaxAMaps];
   CUtensorMap bmap64;
   CUtensorMap bmap16;
+  CUtensorMap bmap64_lo;    // same tensor as bmap64 with a box of lo_rows rows (lo-product stages use fewer rows)
+  int32_t lo_rows;          // rows per CTA of a lo stage (0: lo stages use bmap64)
   int32_t n_par;            // 1, or 8 for the x2 up-sampling conv (one parity per item)
   int32_t par_brow_step;    // B rows between parities
   int32_t out_w, out_h, out_d;         // extent of the tile space
@@ -152,7 +157,16 @@ struct ConvCfg {
 #endif
 constexpr bool kBaseOffsetMode = NBE_BASE_OFFSET != 0;
 
-template <int NRS, int DC, int TM, bool FINAL, bool PAIR = false>
+// EARLY (only with the per-kd accumulator layout [y0 | dy | y1 | y2], one TMEM stage): fine-grained
+// accumulator hand-over.  The issuers order an item as  lo products (-> y0) | kd 0 (+ folded skip)
+// -> (y0, dy) | kd 1 -> (dy, y1) | kd 2 -> (y2, dy)  and commit y0_full / y1_full as soon as the
+// last MMA writing y0 / y1 has been issued; the epilogue drains y0 and y1 into registers while
+// the later kd-planes are still being multiplied, and only (y2, dy) are left when the item ends.
+// The next item's lo products need nothing but y0 (already drained and re-zeroed), so they run
+// under the epilogue's math and stores: the single-buffered TMEM no longer idles the tensor pipe.
+// Same MMAs per accumulator in the same order and the same (y0 + y1) + y2 sum: bit-identical to the
+// plain acc3 path.
+template <int NRS, int DC, int TM, bool FINAL, bool PAIR = false, bool EARLY = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupTable gt,
                 const __grid_constant__ FinalArgs fa) {
@@ -170,7 +184,11 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
   uint64_t* b_empty = b_full + Cfg::kNB;
   uint64_t* acc_full = b_empty + Cfg::kNB;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* y0_full = acc_empty + 2;       // EARLY only
+  uint64_t* y1_full = y0_full + 1;
+  uint64_t* y0_empty = y1_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y0_empty + 1);
+  static_assert(!EARLY || (Cfg::kNBuf == 1 && !FINAL && TM * DC == 512), "EARLY: single-stage acc3 instances only");
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);   // up to 128 floats
 
   const int warp = threadIdx.x >> 5;
@@ -194,6 +212,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     for (int i = 0; i < Cfg::kNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], kIssuers); }
     for (int i = 0; i < Cfg::kNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], kIssuers); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], kIssuers); mbar_init(&acc_empty[i], PAIR ? 512 : 256); }
+    mbar_init(y0_full, kIssuers); mbar_init(y1_full, kIssuers); mbar_init(y0_empty, PAIR ? 512 : 256);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -297,13 +316,15 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
       const int par_brow_step = L->par_brow_step;
+      const int lo_rows = L->lo_rows;
       for (long long it0 = item_first; it0 < n_items; it0 += gridDim.x) {
         int par, w0, h0, d0;
         decode(it0, par, w0, h0, d0);
         for (int g = 0; g < n_groups; ++g) {
           const GroupDesc& G = gt.g[g];
-          const CUtensorMap* bm = G.kc16 ? &L->bmap16 : &L->bmap64;
-          const uint32_t bytes = Cfg::kBRows * (G.kc16 ? 32u : 128u);
+          const bool lo_box = G.lo_stage != 0 && lo_rows > 0;
+          const CUtensorMap* bm = G.kc16 ? &L->bmap16 : (lo_box ? &L->bmap64_lo : &L->bmap64);
+          const uint32_t bytes = lo_box ? static_cast<uint32_t>(lo_rows) * 128u : Cfg::kBRows * (G.kc16 ? 32u : 128u);
           const int row0 = G.brow0 + par * par_brow_step + (PAIR ? static_cast<int>(rank) * Cfg::kBRows : 0);
           const int tps = G.tps;
           for (int j = 0; j < G.ntaps; j += tps) {
@@ -343,12 +364,21 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0, buf = 0, pacc = 0;
     for (long long item = item_first; item < n_items && (!PAIR || rank == 0); item += gridDim.x) {
-      mbar_wait(&acc_empty[buf], pacc ^ 1);
-      tc_fence_after();
+      if constexpr (!EARLY) {
+        mbar_wait(&acc_empty[buf], pacc ^ 1);
+        tc_fence_after();
+      }
       const bool dead = tile_dead(item, my_tile);
       for (int g = 0; g < n_groups; ++g) {
         const GroupDesc& G = gt.g[g];
         const int ntaps = G.ntaps, n_ops = G.n_ops;
+        if constexpr (EARLY) {
+          const int pw = G.pre_wait;
+          if (pw != 0) {
+            mbar_wait(pw == 1 ? y0_empty : &acc_empty[0], pacc ^ 1);
+            tc_fence_after();
+          }
+        }
         const bool k16 = G.kc16 != 0;
         const uint32_t rowb = k16 ? 32u : 128u;
         const uint32_t row16 = rowb >> 4;                       // one row in 16-byte units
@@ -448,7 +478,12 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
             if (++sb == Cfg::kNB) { sb = 0; pb ^= 1; }
           }
         }
-        if (elect_one()) commit(&a_empty[sa]);
+        const int ps = EARLY ? G.post_sig : 0;
+        if (elect_one()) {
+          commit(&a_empty[sa]);
+          if (ps == 1) commit(y0_full);
+          else if (ps == 2) commit(y1_full);
+        }
         __syncwarp();
         if (++sa == Cfg::kNA) { sa = 0; pa ^= 1; }
       }
@@ -475,6 +510,106 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     __half* const out_l_ptr = L->out_l_ptr;
     __half* const out_d_ptr = L->out_d_ptr;
     uint32_t buf = 0, pacc = 0;
+    if constexpr (EARLY) {
+      // [y0 | dy | y1 | y2] x COUT columns per tile; this thread owns row r of tile t and the two
+      // 32-channel chunks ch(0), ch(1) (TM == 1: the warp sets take alternate chunks of the 128)
+      constexpr int COUT = DC / 4;
+      const int t = TM == 2 ? eg : 0;
+      auto ch = [&](int i) { return TM == 1 ? eg * 32 + 64 * i : 32 * i; };
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * DC;
+      auto arrive = [](uint64_t* bar) {
+        if constexpr (PAIR) mbar_arrive_leader(bar); else mbar_arrive(bar);
+      };
+      for (long long it0 = item_first; it0 < n_items; it0 += gridDim.x) {
+        const long long item = it0 + rank;
+        const bool item_ok = item < n_items;
+        int par, w0, h0, d0;
+        decode(item_ok ? item : 0, par, w0, h0, d0);
+        const bool dead = tile_dead(it0, eg);     // nothing is accumulated into a dead tile: its columns stay zero
+        const int w = w0 + (r & 7);
+        const int h = h0 + t * 16 + (r >> 3);
+        const bool valid = item_ok && (w < out_w) && (h < out_h);
+        uint32_t ps[64];
+        // ---- y0: complete once the kd = 0 groups are done (two more kd-planes of MMAs still to come)
+        mbar_wait(y0_full, pacc);
+        tc_fence_after();
+        if (!dead) {
+          tmem_ld32(taddr + ch(0), ps);
+          tmem_ld32(taddr + ch(1), ps + 32);
+          tmem_ld_wait();
+          tmem_st32_zero(taddr + ch(0));
+          tmem_st32_zero(taddr + ch(1));
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        arrive(y0_empty);                         // the next item's lo products may start
+        // ---- y1
+        mbar_wait(y1_full, pacc);
+        tc_fence_after();
+        if (!dead) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            uint32_t y1[32];
+            tmem_ld32(taddr + 2 * COUT + ch(i), y1);
+            tmem_ld_wait();
+            tmem_st32_zero(taddr + 2 * COUT + ch(i));
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              ps[32 * i + j] = __float_as_uint(__uint_as_float(ps[32 * i + j]) + __uint_as_float(y1[j]));
+          }
+        }
+        // ---- y2, dy: end of the item
+        mbar_wait(&acc_full[0], pacc);
+        tc_fence_after();
+        if (!dead) {
+          const int64_t voff = static_cast<int64_t>(d0) * out_sd + static_cast<int64_t>(h) * out_sh +
+                               static_cast<int64_t>(w) * out_sw;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const int c = ch(i) + 16 * hf;
+              uint32_t y2[16], dy[16];
+              tmem_ld16(taddr + 3 * COUT + c, y2);
+              tmem_ld16(taddr + COUT + c, dy);
+              tmem_ld_wait();
+              tmem_st16_zero(taddr + 3 * COUT + c);
+              tmem_st16_zero(taddr + COUT + c);
+              uint32_t ph[8], pl[8], pd[8];
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                float y0v = (__uint_as_float(ps[32 * i + 16 * hf + j]) + __uint_as_float(y2[j])) * kInvWeightScale + bias_s[c + j];
+                float y1v = (__uint_as_float(ps[32 * i + 16 * hf + j + 1]) + __uint_as_float(y2[j + 1])) * kInvWeightScale + bias_s[c + j + 1];
+                float d0v = __uint_as_float(dy[j]) * kInvWeightScale;
+                float d1v = __uint_as_float(dy[j + 1]) * kInvWeightScale;
+                if (act) {
+                  d0v = y0v > 0.f ? d0v : 0.01f * d0v;
+                  d1v = y1v > 0.f ? d1v : 0.01f * d1v;
+                  y0v = y0v >= 0.f ? y0v : 0.01f * y0v;
+                  y1v = y1v >= 0.f ? y1v : 0.01f * y1v;
+                }
+                const __half2 hh = __floats2half2_rn(y0v, y1v);
+                const float2 hf2 = __half22float2(hh);
+                const __half2 ll = __floats2half2_rn(y0v - hf2.x, y1v - hf2.y);
+                const __half2 dd = __floats2half2_rn(d0v, d1v);
+                ph[j >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+                pl[j >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
+                pd[j >> 1] = *reinterpret_cast<const uint32_t*>(&dd);
+              }
+              if (valid) {
+                st_global_v8(out_h_ptr + voff + c, make_uint4(ph[0], ph[1], ph[2], ph[3]), make_uint4(ph[4], ph[5], ph[6], ph[7]));
+                st_global_v8(out_l_ptr + voff + c, make_uint4(pl[0], pl[1], pl[2], pl[3]), make_uint4(pl[4], pl[5], pl[6], pl[7]));
+                st_global_v8(out_d_ptr + voff + c, make_uint4(pd[0], pd[1], pd[2], pd[3]), make_uint4(pd[4], pd[5], pd[6], pd[7]));
+              }
+            }
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        arrive(&acc_empty[0]);
+        pacc ^= 1;
+      }
+    } else
     for (long long it0 = item_first; it0 < n_items; it0 += gridDim.x) {
       const long long item = it0 + rank;
       const bool item_ok = item < n_items;

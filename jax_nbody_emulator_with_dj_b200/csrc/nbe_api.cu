@@ -8,12 +8,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "aux_kernels.cuh"
@@ -29,8 +31,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 enum ConvType { T_CONV3 = 0, T_SKIP1 = 1, T_DOWN = 2, T_UP = 3 };
-enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_PAIR_256_512_1, I_PAIR_128_128_2, I_PAIR_256_256_1, I_PAIR_128_256_1, I_COUNT };
-struct InstInfo { int nrs, dc, tm; bool fin; bool pair = false; bool acc3 = false; };
+enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_PAIR_256_512_1, I_PAIR_128_128_2, I_PAIR_256_256_1, I_PAIR_128_256_1, I_EARLY_128_256_2, I_EARLY_256_512_1, I_COUNT };
+struct InstInfo { int nrs, dc, tm; bool fin; bool pair = false; bool acc3 = false; bool early = false; };
 const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32, 16, 2, true},
                                  {128, 64, 2, false},  {64, 64, 2, false},   {256, 128, 1, false},
                                  {128, 256, 2, false, false, true}, {256, 512, 1, false, false, true},
@@ -38,7 +40,9 @@ const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32
                                  {192, 256, 2, false, true, true}, {384, 512, 1, false, true, true},
                                  {192, 128, 2, false, true}, {384, 256, 1, false, true},
                                  // one tile per CTA, two accumulator stages: the acc3 epilogue overlaps the next item
-                                 {192, 256, 1, false, true, true}};
+                                 {192, 256, 1, false, true, true},
+                                 // early-drain acc3 pair instances (fine-grained accumulator hand-over, conv_mma.cuh)
+                                 {192, 256, 2, false, true, true, true}, {384, 512, 1, false, true, true, true}};
 
 // activation tensors of the net
 enum ActId {
@@ -97,13 +101,17 @@ struct nbe_ctx {
   int num_sms = 148;
   std::string err;
   EncodeTiledFn encode = nullptr;
-  cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+  cudaStream_t own_stream = nullptr, copy_stream = nullptr, up_stream = nullptr;
+  cudaEvent_t mod_done = nullptr;   // recorded after the modulation kernel; every consumer stream waits on it
+  bool mod_pending = false;
 
   bool have_params = false, premod = false, vel = true;
   float eps = 1e-8f;
   int precision = NBE_PREC_SPLIT;
   bool pair = true;         // CTA pairs (cta_group::2) for the 3^3 velocity launches (NBE_PAIR=0 disables)
   bool dbuf = false;        // 64-output acc3 pair launches: one tile per CTA + double-buffered TMEM (NBE_DBUF=0: two tiles)
+  bool early = true;        // acc3 pair launches hand the per-kd accumulators over as they complete (NBE_EARLY=0: whole item)
+  bool lo_box = true;       // lo-product weight stages are loaded with a box of only the rows they use (NBE_LOBOX=0)
   int band_h = 2;           // tile rows per h-band of the item order (NBE_BAND; 0: whole planes)
   bool wide16 = true;       // also for the 16-channel first layer (32-byte rows, SWIZZLE_32B row shifts; NBE_WIDE16)
   bool wide = true;         // w-halo'd activation blocks serving 9 taps per load (NBE_WIDE=0 disables)
@@ -165,6 +173,23 @@ int fail(nbe_ctx* c, int code, const char* fmt, ...) {
   } while (0)
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Every entry point runs on its context's device and restores the caller's current device on exit
+// (the host process may drive several GPUs, one context each, and PyTorch tracks the current device
+// per thread).
+struct DevGuard {
+  int prev = -1;
+  cudaError_t err;
+  explicit DevGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    err = (prev == dev) ? cudaSuccess : cudaSetDevice(dev);
+  }
+  ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ENTER_DEVICE(ctx)                                                                          \
+  DevGuard dev_guard_((ctx)->device);                                                              \
+  if (dev_guard_.err != cudaSuccess)                                                               \
+    return fail((ctx), NBE_ERR_CUDA, "cudaSetDevice(%d) -> %s", (ctx)->device, cudaGetErrorString(dev_guard_.err))
 
 int ensure(nbe_ctx* ctx, void** p, size_t* cap, size_t need) {
   if (*cap >= need && *p) return NBE_OK;
@@ -241,8 +266,8 @@ int build_static(nbe_ctx* ctx) {
       bool ok = ctx->wide && vel;
       for (auto& p : s.parts) ok = ok && (p.type == T_CONV3 || p.type == T_SKIP1);
       if (!ok) continue;
-      if (s.inst == I_128_256_2) s.inst = ctx->dbuf ? I_PAIR_128_256_1 : I_PAIR_128_256_2;
-      else if (s.inst == I_256_512_1) s.inst = I_PAIR_256_512_1;
+      if (s.inst == I_128_256_2) s.inst = ctx->dbuf ? I_PAIR_128_256_1 : (ctx->early ? I_EARLY_128_256_2 : I_PAIR_128_256_2);
+      else if (s.inst == I_256_512_1) s.inst = ctx->early ? I_EARLY_256_512_1 : I_PAIR_256_512_1;
       else if (s.inst == I_128_128_2) s.inst = I_PAIR_128_128_2;
       else if (s.inst == I_256_256_1) s.inst = I_PAIR_256_256_1;
     }
@@ -514,14 +539,25 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
       const int box_rows = ii.pair ? ii.nrs / 2 : ii.nrs;
       if ((rc = make_b_map(ctx, &Lc.bmap64, packed + s.b64_off, 64, static_cast<long long>(s.n_tiles64) * ii.nrs, box_rows)) ||
           (rc = make_b_map16(ctx, &Lc.bmap16, packed + s.b16_off, s.n_tiles16, ii.nrs, box_rows))) { delete P; return rc; }
+      // pair acc3 layout: a lo stage [Wl half | Wh half] fills only the first `cout` of the 1.5 x cout rows
+      // each CTA owns per stage; loading just those saves a sixth of the weight traffic
+      Lc.lo_rows = 0;
+      memset(&Lc.bmap64_lo, 0, sizeof Lc.bmap64_lo);
+      if (ctx->lo_box && ii.pair && ii.acc3 && s.n_tiles64 > 0) {
+        Lc.lo_rows = s.cout;
+        if ((rc = make_b_map(ctx, &Lc.bmap64_lo, packed + s.b64_off, 64, static_cast<long long>(s.n_tiles64) * ii.nrs, s.cout))) { delete P; return rc; }
+      }
 
       int ng = 0;
       bool bad = false;
       // lo-product groups are issued before the main groups (see conv_mma.cuh: truncating
       // accumulation), so collect them separately
-      std::vector<GroupDesc> g_lo, g_main;
-      int cur_kind = 0;
-      auto push = [&](const GroupDesc& G) { (cur_kind == 1 ? g_lo : g_main).push_back(G); };
+      // main groups are further ordered by the accumulator they complete: kd 0 and the folded skip
+      // (y0, dy) | kd 1 (dy, y1) | kd 2 (y2, dy), which is what lets the EARLY instances drain y0 / y1
+      // while later kd-planes are still running
+      std::vector<GroupDesc> g_lo, g_main[3];
+      int cur_kind = 0, cur_kd = 0;
+      auto push = [&](const GroupDesc& G) { (cur_kind == 1 ? g_lo : g_main[cur_kd]).push_back(G); };
       const int nkind = (vel && split) ? 2 : 1;
       const ActBuf& OB = P->act[s.out_act];
       // tile space = output voxels, except for the up-sampling conv (input voxels)
@@ -651,6 +687,8 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           G.tps = static_cast<int8_t>((k16 && ntaps >= 3) ? 3 : 1);
           cur_box_w = G.pitch;
           cur_kind = k16 ? 0 : kind;
+          cur_kd = (ii.acc3 && !k16 && kd > 0) ? kd : 0;
+          G.lo_stage = (cur_kind == 1) ? 1 : 0;
           fill_ops(G, kind, sc, par, kd);
           if (G.a_map[0] < 0 || (G.n_a == 2 && G.a_map[1] < 0)) bad = true;
           push(G);
@@ -682,8 +720,18 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           H.flops += 2.0 * ly.cout * ly.cin * vout * m;
         }
       }
+      if (ii.early) {
+        if (g_lo.empty() || g_main[0].empty() || g_main[1].empty() || g_main[2].empty()) bad = true;
+        else {
+          g_lo.front().pre_wait = 1;            // lo products accumulate into y0
+          g_main[0].front().pre_wait = 2;       // first MMA touching dy
+          g_main[0].back().post_sig = 1;        // y0 complete
+          g_main[1].back().post_sig = 2;        // y1 complete
+        }
+      }
       for (const auto& G : g_lo) { if (ng < kMaxGroups) H.G.g[ng++] = G; else bad = true; }
-      for (const auto& G : g_main) { if (ng < kMaxGroups) H.G.g[ng++] = G; else bad = true; }
+      for (int kq = 0; kq < 3; ++kq)
+        for (const auto& G : g_main[kq]) { if (ng < kMaxGroups) H.G.g[ng++] = G; else bad = true; }
       if (bad) { delete P; return fail(ctx, NBE_ERR_STATE, "launch %s: too many groups / tensor maps", s.name.c_str()); }
       H.G.n_groups = ng;
       Lc.cout = s.cout; Lc.vel = vel ? 1 : 0; Lc.act = 1;
@@ -723,30 +771,35 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
   return NBE_OK;
 }
 
+// The opt-in to > 48 KB of dynamic shared memory is per function AND per device: one process may
+// drive several GPUs (nbe_process_box_multi), each from its own host thread.
+template <class K>
+cudaError_t opt_in_smem(K kern, int bytes, int device, std::atomic<uint64_t>& done) {
+  const uint64_t bit = 1ull << (device & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
+
 template <int NRS, int DC, int TM, bool FIN>
-cudaError_t launch_inst(const ConvLaunch* dl, const GroupTable& gt, const FinalArgs& fa, int grid, cudaStream_t st) {
+cudaError_t launch_inst(int device, const ConvLaunch* dl, const GroupTable& gt, const FinalArgs& fa, int grid, cudaStream_t st) {
   using Cfg = ConvCfg<NRS, DC, TM>;
-  static bool attr_set = false;
+  static std::atomic<uint64_t> done{0};
   auto kern = conv_mma_kernel<NRS, DC, TM, FIN>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  cudaError_t e = opt_in_smem(kern, Cfg::kSmemBytes, device, done);
+  if (e != cudaSuccess) return e;
   kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(dl, gt, fa);
   return cudaGetLastError();
 }
 
-template <int NRS, int DC, int TM>
-cudaError_t launch_pair(const ConvLaunch* dl, const GroupTable& gt, const FinalArgs& fa, int grid, cudaStream_t st) {
+template <int NRS, int DC, int TM, bool EARLY = false>
+cudaError_t launch_pair(int device, const ConvLaunch* dl, const GroupTable& gt, const FinalArgs& fa, int grid, cudaStream_t st) {
   using Cfg = ConvCfg<NRS, DC, TM, true>;
-  static bool attr_set = false;
-  auto kern = conv_mma_kernel<NRS, DC, TM, false, true>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> done{0};
+  auto kern = conv_mma_kernel<NRS, DC, TM, false, true, EARLY>;
+  cudaError_t e = opt_in_smem(kern, Cfg::kSmemBytes, device, done);
+  if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -756,21 +809,23 @@ cudaError_t launch_pair(const ConvLaunch* dl, const GroupTable& gt, const FinalA
   return cudaLaunchKernelEx(&cfg, kern, dl, gt, fa);
 }
 
-cudaError_t launch_conv(int inst, const ConvLaunch* dl, const GroupTable& gt, const FinalArgs& fa, int grid, cudaStream_t st) {
+cudaError_t launch_conv(int device, int inst, const ConvLaunch* dl, const GroupTable& gt, const FinalArgs& fa, int grid, cudaStream_t st) {
   switch (inst) {
-    case I_128_128_2: return launch_inst<128, 128, 2, false>(dl, gt, fa, grid, st);
-    case I_256_256_1: return launch_inst<256, 256, 1, false>(dl, gt, fa, grid, st);
-    case I_FINAL: return launch_inst<32, 16, 2, true>(dl, gt, fa, grid, st);
-    case I_128_64_2: return launch_inst<128, 64, 2, false>(dl, gt, fa, grid, st);
-    case I_64_64_2: return launch_inst<64, 64, 2, false>(dl, gt, fa, grid, st);
-    case I_256_128_2: return launch_inst<256, 128, 1, false>(dl, gt, fa, grid, st);
-    case I_128_256_2: return launch_inst<128, 256, 2, false>(dl, gt, fa, grid, st);
-    case I_256_512_1: return launch_inst<256, 512, 1, false>(dl, gt, fa, grid, st);
-    case I_PAIR_128_256_2: return launch_pair<192, 256, 2>(dl, gt, fa, grid, st);
-    case I_PAIR_256_512_1: return launch_pair<384, 512, 1>(dl, gt, fa, grid, st);
-    case I_PAIR_128_128_2: return launch_pair<192, 128, 2>(dl, gt, fa, grid, st);
-    case I_PAIR_256_256_1: return launch_pair<384, 256, 1>(dl, gt, fa, grid, st);
-    case I_PAIR_128_256_1: return launch_pair<192, 256, 1>(dl, gt, fa, grid, st);
+    case I_128_128_2: return launch_inst<128, 128, 2, false>(device, dl, gt, fa, grid, st);
+    case I_256_256_1: return launch_inst<256, 256, 1, false>(device, dl, gt, fa, grid, st);
+    case I_FINAL: return launch_inst<32, 16, 2, true>(device, dl, gt, fa, grid, st);
+    case I_128_64_2: return launch_inst<128, 64, 2, false>(device, dl, gt, fa, grid, st);
+    case I_64_64_2: return launch_inst<64, 64, 2, false>(device, dl, gt, fa, grid, st);
+    case I_256_128_2: return launch_inst<256, 128, 1, false>(device, dl, gt, fa, grid, st);
+    case I_128_256_2: return launch_inst<128, 256, 2, false>(device, dl, gt, fa, grid, st);
+    case I_256_512_1: return launch_inst<256, 512, 1, false>(device, dl, gt, fa, grid, st);
+    case I_PAIR_128_256_2: return launch_pair<192, 256, 2>(device, dl, gt, fa, grid, st);
+    case I_PAIR_256_512_1: return launch_pair<384, 512, 1>(device, dl, gt, fa, grid, st);
+    case I_PAIR_128_128_2: return launch_pair<192, 128, 2>(device, dl, gt, fa, grid, st);
+    case I_PAIR_256_256_1: return launch_pair<384, 256, 1>(device, dl, gt, fa, grid, st);
+    case I_PAIR_128_256_1: return launch_pair<192, 256, 1>(device, dl, gt, fa, grid, st);
+    case I_EARLY_128_256_2: return launch_pair<192, 256, 2, true>(device, dl, gt, fa, grid, st);
+    case I_EARLY_256_512_1: return launch_pair<384, 512, 1, true>(device, dl, gt, fa, grid, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -781,7 +836,7 @@ int run_sample(nbe_ctx* ctx, Plan* P, int sample, PackArgs pk, FinalArgs fa, cud
   pk.out = reinterpret_cast<__half*>(ctx->arena + P->act[A_IN16].off_hi);
   pk.n0 = P->dims[0]; pk.n1 = P->dims[1]; pk.n2 = P->dims[2];
   const long long nvox = 1ll * pk.n0 * pk.n1 * pk.n2;
-  const int pgrid = static_cast<int>(std::min<long long>((nvox + 255) / 256, 148ll * 16));
+  const int pgrid = static_cast<int>(std::min<long long>((nvox + 255) / 256, 16ll * ctx->num_sms));
   const int slots = P->n_launch + 1;
   const bool prof = ctx->profiling && ctx->prof_events.size() < 400000;
   if (prof && static_cast<int>(ctx->prof_names.size()) != slots) {
@@ -797,6 +852,7 @@ int run_sample(nbe_ctx* ctx, Plan* P, int sample, PackArgs pk, FinalArgs fa, cud
   auto mark = [&]() {
     if (prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ctx->prof_events.push_back(e); }
   };
+  if (ctx->mod_pending) CK(cudaStreamWaitEvent(st, ctx->mod_done, 0));
   mark();
   pack_input_kernel<<<pgrid, 256, 0, st>>>(pk);
   CK(cudaGetLastError());
@@ -804,7 +860,7 @@ int run_sample(nbe_ctx* ctx, Plan* P, int sample, PackArgs pk, FinalArgs fa, cud
   mark();
   for (int li = 0; li < P->n_launch; ++li) {
     const HostLaunch& H = P->launches[static_cast<size_t>(sample) * P->n_launch + li];
-    CK(launch_conv(H.inst, P->dev_launches + static_cast<size_t>(sample) * P->n_launch + li, H.G, fa, H.grid, st));
+    CK(launch_conv(ctx->device, H.inst, P->dev_launches + static_cast<size_t>(sample) * P->n_launch + li, H.G, fa, H.grid, st));
     ctx->launches++;
     mark();
   }
@@ -849,7 +905,7 @@ template <class After>
 int process_box_core(nbe_ctx* ctx, const void* box_dev, int in_dtype, const int32_t size[3], const int32_t size_out[3],
                      const int32_t crop[3], const int32_t plen[3], const int32_t* crop_idx, const int32_t* add_idx0, int sub_first,
                      int sub_count, float Dz, float vel_fac, void* disp_dev, void* vel_dev, int out_dtype,
-                     cudaStream_t st, After after) {
+                     cudaStream_t st, After after, bool blocks = false, cudaEvent_t first_wait = nullptr) {
   const int64_t S0 = size[0], S1 = size[1], S2 = size[2];
   const int64_t O0 = size_out[0], O1 = size_out[1], O2 = size_out[2];
   int rc;
@@ -859,6 +915,7 @@ int process_box_core(nbe_ctx* ctx, const void* box_dev, int in_dtype, const int3
   CK(cudaMemcpyAsync(ctx->d_idx, crop_idx + static_cast<size_t>(sub_first) * per, idx_bytes, cudaMemcpyHostToDevice, st));
   Plan* P = nullptr;
   if ((rc = build_plan(ctx, plen, 1, &P))) return rc;
+  if (first_wait) CK(cudaStreamWaitEvent(st, first_wait, 0));
   const size_t es = dtype_size(out_dtype);
   for (int s = 0; s < sub_count; ++s) {
     const int32_t* ai = add_idx0 + static_cast<size_t>(sub_first + s) * 3;
@@ -870,10 +927,21 @@ int process_box_core(nbe_ctx* ctx, const void* box_dev, int in_dtype, const int3
     FinalArgs fa{};
     fa.src = box_dev; fa.src_dtype = in_dtype; fa.src_sc = pk.src_sc; fa.src_sd = pk.src_sd; fa.src_sh = pk.src_sh;
     fa.idx_d = pk.idx_d + 48; fa.idx_h = pk.idx_h + 48; fa.idx_w = pk.idx_w + 48;
-    const size_t base = (static_cast<size_t>(ai[0]) * O1 + ai[1]) * O2 + ai[2];
-    fa.disp = static_cast<uint8_t*>(disp_dev) + base * es;
-    fa.vel = ctx->vel ? static_cast<uint8_t*>(vel_dev) + base * es : nullptr;
-    fa.out_dtype = out_dtype; fa.mid_dtype = in_dtype; fa.o_sc = O0 * O1 * O2; fa.o_sd = O1 * O2; fa.o_sh = O2;
+    if (blocks) {
+      // block layout [sub_count][3][c0][c1][c2]: each subbox's output is one contiguous record (the
+      // unit of the NCCL all-gather of a sharded box)
+      const int64_t c0 = crop[0], c1 = crop[1], c2 = crop[2];
+      const size_t base = static_cast<size_t>(s) * 3 * c0 * c1 * c2;
+      fa.disp = static_cast<uint8_t*>(disp_dev) + base * es;
+      fa.vel = ctx->vel ? static_cast<uint8_t*>(vel_dev) + base * es : nullptr;
+      fa.o_sc = c0 * c1 * c2; fa.o_sd = c1 * c2; fa.o_sh = c2;
+    } else {
+      const size_t base = (static_cast<size_t>(ai[0]) * O1 + ai[1]) * O2 + ai[2];
+      fa.disp = static_cast<uint8_t*>(disp_dev) + base * es;
+      fa.vel = ctx->vel ? static_cast<uint8_t*>(vel_dev) + base * es : nullptr;
+      fa.o_sc = O0 * O1 * O2; fa.o_sd = O1 * O2; fa.o_sh = O2;
+    }
+    fa.out_dtype = out_dtype; fa.mid_dtype = in_dtype;
     fa.in_norm = pk.in_norm; fa.six = 6.0f; fa.dx_norm = vel_fac * 6.0f; fa.x0_norm = vel_fac * 6.0f / Dz;
     if ((rc = run_sample(ctx, P, 0, pk, fa, st))) return rc;
     if ((rc = after(s))) return rc;
@@ -898,6 +966,25 @@ int check_box_args(nbe_ctx* ctx, const void* in, const int32_t* size, const int3
   return NBE_OK;
 }
 
+// The gather tables and paste anchors index host and device memory: reject anything out of range
+// before a copy or a launch is enqueued (O(n_sub * plen), negligible).
+int check_tables(nbe_ctx* ctx, const int32_t* size, const int32_t* crop, const int32_t* plen, const int32_t* crop_idx,
+                 const int32_t* add_idx0, int sub_first, int sub_count) {
+  if (sub_first < 0) return fail(ctx, NBE_ERR_ARG, "sub_first < 0");
+  const int per = plen[0] + plen[1] + plen[2];
+  for (int s = sub_first; s < sub_first + sub_count; ++s) {
+    const int32_t* t = crop_idx + static_cast<size_t>(s) * per;
+    for (int d = 0; d < 3; ++d) {
+      for (int i = 0; i < plen[d]; ++i)
+        if (t[i] < 0 || t[i] >= size[d]) return fail(ctx, NBE_ERR_ARG, "crop_idx of subbox %d, dim %d out of range: %d", s, d, t[i]);
+      t += plen[d];
+      const int32_t a = add_idx0[static_cast<size_t>(s) * 3 + d];
+      if (a < 0 || a + crop[d] > size[d]) return fail(ctx, NBE_ERR_ARG, "add_idx0 of subbox %d, dim %d out of range: %d", s, d, a);
+    }
+  }
+  return NBE_OK;
+}
+
 
 }  // namespace
 
@@ -913,8 +1000,8 @@ int nbe_create(nbe_ctx** out, int device) {
   *out = nullptr;
   nbe_ctx* ctx = new nbe_ctx();
   ctx->device = device;
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) { delete ctx; return NBE_ERR_CUDA; }
+  DevGuard dev_guard_(device);
+  if (dev_guard_.err != cudaSuccess) { delete ctx; return NBE_ERR_CUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return NBE_ERR_CUDA; }
   if (prop.major != 10) { delete ctx; return NBE_ERR_UNSUPPORTED; }
@@ -929,17 +1016,21 @@ int nbe_create(nbe_ctx** out, int device) {
   if (const char* e = getenv("NBE_WIDE")) ctx->wide = atoi(e) != 0;
   if (const char* e = getenv("NBE_PAIR")) ctx->pair = atoi(e) != 0;
   if (const char* e = getenv("NBE_DBUF")) ctx->dbuf = atoi(e) != 0;
+  if (const char* e = getenv("NBE_EARLY")) ctx->early = atoi(e) != 0;
+  if (const char* e = getenv("NBE_LOBOX")) ctx->lo_box = atoi(e) != 0;
   if (const char* e = getenv("NBE_WIDE16")) ctx->wide16 = atoi(e) != 0;
   if (const char* e = getenv("NBE_BAND")) ctx->band_h = atoi(e);
   cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->mod_done, cudaEventDisableTiming);
   *out = ctx;
   return NBE_OK;
 }
 
 void nbe_destroy(nbe_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  DevGuard dev_guard_(ctx->device);
   cudaDeviceSynchronize();
   for (auto* p : ctx->plans) { if (p->dev_launches) cudaFree(p->dev_launches); delete p; }
   for (auto& l : ctx->layers) { cudaFree(l.W); cudaFree(l.dW); cudaFree(l.SW); cudaFree(l.sb); }
@@ -948,6 +1039,8 @@ void nbe_destroy(nbe_ctx* ctx) {
   cudaFree(ctx->d_disp); cudaFree(ctx->d_velo); cudaFree(ctx->d_idx);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
+  if (ctx->mod_done) cudaEventDestroy(ctx->mod_done);
   delete ctx;
 }
 
@@ -956,7 +1049,7 @@ const char* nbe_last_error(const nbe_ctx* ctx) { return ctx ? ctx->err.c_str() :
 int nbe_set_precision(nbe_ctx* ctx, int precision) {
   if (!ctx) return NBE_ERR_ARG;
   if (precision != NBE_PREC_SPLIT && precision != NBE_PREC_FP16) return fail(ctx, NBE_ERR_ARG, "unknown precision %d", precision);
-  CK(cudaSetDevice(ctx->device));
+  ENTER_DEVICE(ctx);
   if (precision == ctx->precision) return NBE_OK;
   ctx->precision = precision;
   if (ctx->have_params) { CK(cudaDeviceSynchronize()); return build_static(ctx); }
@@ -966,7 +1059,7 @@ int nbe_set_precision(nbe_ctx* ctx, int precision) {
 int nbe_set_params(nbe_ctx* ctx, const nbe_layer_params* layers, int n_layers, int premodulated, int compute_vel,
                    float eps) {
   if (!ctx || !layers) return NBE_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
+  ENTER_DEVICE(ctx);
   CK(cudaDeviceSynchronize());
   if (n_layers != 33) return fail(ctx, NBE_ERR_ARG, "expected 33 conv layers, got %d", n_layers);
   for (auto& l : ctx->layers) { cudaFree(l.W); cudaFree(l.dW); cudaFree(l.SW); cudaFree(l.sb); }
@@ -1003,7 +1096,7 @@ int nbe_modulate(nbe_ctx* ctx, const float* Om, const float* Dz, int batch, void
   if (!ctx->have_params) return fail(ctx, NBE_ERR_STATE, "nbe_modulate before nbe_set_params");
   if (batch < 1 || !Dz) return fail(ctx, NBE_ERR_ARG, "batch >= 1 and Dz required");
   if (!ctx->premod && !Om) return fail(ctx, NBE_ERR_ARG, "Om required for style models");
-  CK(cudaSetDevice(ctx->device));
+  ENTER_DEVICE(ctx);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t need_p = static_cast<size_t>(batch) * ctx->packed_halves * 2;
   const size_t need_w = static_cast<size_t>(batch) * ctx->w32_floats * 4;
@@ -1053,6 +1146,10 @@ int nbe_modulate(nbe_ctx* ctx, const float* Om, const float* Dz, int batch, void
   CK(cudaStreamSynchronize(st));     // hm / s0 / s1 are stack-owned
   modulate_kernel<<<dim3(rows, batch), 128, 0, st>>>(ctx->d_metas, static_cast<int>(hm.size()), ctx->d_s0, ctx->d_s1, ctx->eps);
   CK(cudaGetLastError());
+  // the packed weights are consumed on other streams (the caller's in nbe_forward, the context's own
+  // in nbe_process_box): they wait on this event instead of relying on stream coincidence
+  CK(cudaEventRecord(ctx->mod_done, st));
+  ctx->mod_pending = true;
   ctx->launches++;
   ctx->mod_batch = batch;
   return NBE_OK;
@@ -1063,7 +1160,7 @@ int nbe_get_modulated(nbe_ctx* ctx, int layer_index, int sample, float* w_host, 
   if (ctx->mod_batch < 1) return fail(ctx, NBE_ERR_STATE, "nbe_get_modulated before nbe_modulate");
   if (layer_index < 0 || layer_index >= static_cast<int>(ctx->layers.size()) || sample < 0 || sample >= ctx->mod_batch)
     return fail(ctx, NBE_ERR_ARG, "layer/sample out of range");
-  CK(cudaSetDevice(ctx->device));
+  ENTER_DEVICE(ctx);
   CK(cudaDeviceSynchronize());
   const Layer& ly = ctx->layers[layer_index];
   const size_t n = static_cast<size_t>(ly.cout) * ly.cin * ly.k * ly.k * ly.k;
@@ -1100,7 +1197,7 @@ int nbe_forward(nbe_ctx* ctx, const void* x_dev, int in_dtype, int batch, const 
   if (!ctx->vel && vel_dev) return fail(ctx, NBE_ERR_ARG, "displacement-only model: vel_dev must be NULL");
   if (ctx->mod_batch != 1 && ctx->mod_batch != batch) return fail(ctx, NBE_ERR_STATE, "weights modulated for %d samples, batch is %d", ctx->mod_batch, batch);
   if (in_dtype < 0 || in_dtype > 2 || out_dtype < 0 || out_dtype > 2) return fail(ctx, NBE_ERR_ARG, "bad dtype");
-  CK(cudaSetDevice(ctx->device));
+  ENTER_DEVICE(ctx);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Plan* P = nullptr;
   int rc = build_plan(ctx, dims, batch, &P);
@@ -1136,40 +1233,54 @@ int nbe_process_box_dev(nbe_ctx* ctx, const void* box_dev, int in_dtype, const i
   if (!ctx) return NBE_ERR_ARG;
   int rc = check_box_args(ctx, box_dev, size, crop, plen, crop_idx, add_idx0, disp_dev, vel_dev, sub_count, in_dtype, out_dtype);
   if (rc) return rc;
-  CK(cudaSetDevice(ctx->device));
+  ENTER_DEVICE(ctx);
   return process_box_core(ctx, box_dev, in_dtype, size, size, crop, plen, crop_idx, add_idx0, sub_first, sub_count, Dz,
                           vel_fac, disp_dev, vel_dev, out_dtype, static_cast<cudaStream_t>(stream),
                           [](int) { return NBE_OK; });
 }
 
-int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32_t size[3], const int32_t crop[3],
-                    const int32_t plen[3], const int32_t* crop_idx, const int32_t* add_idx0, int sub_first,
-                    int sub_count, float Dz, float vel_fac, void* disp_host, void* vel_host, int out_dtype) {
-  if (!ctx) return NBE_ERR_ARG;
-  int rc = check_box_args(ctx, in_host, size, crop, plen, crop_idx, add_idx0, disp_host, vel_host, sub_count, in_dtype, out_dtype);
+// SubboxProcessor.process_box on host buffers for one context (see nbe_process_box in nbe.h).  With
+// disp_blk / vel_blk set the results stay on the device in block layout instead of going back to the host.
+static int process_box_host(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32_t size[3], const int32_t crop[3],
+                            const int32_t plen[3], const int32_t* crop_idx, const int32_t* add_idx0, int sub_first,
+                            int sub_count, float Dz, float vel_fac, void* disp_host, void* vel_host, int out_dtype,
+                            void* disp_blk, void* vel_blk) {
+  const bool blocks = disp_blk != nullptr;
+  int rc = check_box_args(ctx, in_host, size, crop, plen, crop_idx, add_idx0, blocks ? disp_blk : disp_host,
+                          blocks ? vel_blk : vel_host, sub_count, in_dtype, out_dtype);
   if (rc) return rc;
   if (sub_count == 0) return NBE_OK;
-  CK(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->own_stream, cs = ctx->copy_stream;
+  if ((rc = check_tables(ctx, size, crop, plen, crop_idx, add_idx0, sub_first, sub_count))) return rc;
+  ENTER_DEVICE(ctx);
+  cudaStream_t st = ctx->own_stream, cs = ctx->copy_stream, us = ctx->up_stream;
   const int64_t S0 = size[0], S1 = size[1], S2 = size[2];
   const int per = plen[0] + plen[1] + plen[2];
   const size_t ies = dtype_size(in_dtype), es = dtype_size(out_dtype);
-  const size_t plane_in = static_cast<size_t>(S1) * S2 * ies, plane_out = static_cast<size_t>(S1) * S2 * es;
+  const size_t plane_out = static_cast<size_t>(S1) * S2 * es;
 
-  // ---- device slabs hold only what this range of subboxes touches.
-  // input: the D-planes it reads (owned slabs + 48-voxel halo, periodic) compacted into slots in
-  // increasing plane order; the D gather tables are remapped plane -> slot.  On 8 ranks that is
-  // ~30 % of the box (upload and memory); it is also what lets a box larger than one GPU's HBM
-  // be processed when sharded (BASELINE config 5).
-  std::vector<int32_t> slot(static_cast<size_t>(S0), -1);
+  // ---- the device holds only the (D, H) window this range of subboxes reads: the D-planes and
+  // H-rows that occur in its gather tables (owned blocks + 48-voxel halo, periodic), compacted into
+  // slots in increasing index order; the tables are remapped index -> slot.  On 8 ranks of the 512^3
+  // box that is 224 x 352 of 512 x 512 rows (30 % of the box); it is also what lets a box larger than
+  // one GPU's HBM be processed when sharded (BASELINE config 5).
+  std::vector<int32_t> slotD(static_cast<size_t>(S0), -1), slotH(static_cast<size_t>(S1), -1);
   std::vector<int32_t> tabs(crop_idx + static_cast<size_t>(sub_first) * per,
                             crop_idx + static_cast<size_t>(sub_first + sub_count) * per);
-  for (int s = 0; s < sub_count; ++s)
-    for (int i = 0; i < plen[0]; ++i) slot[tabs[static_cast<size_t>(s) * per + i]] = 0;
-  int64_t n_slots = 0;
-  for (int64_t d = 0; d < S0; ++d) if (slot[d] == 0) slot[d] = static_cast<int32_t>(n_slots++);
-  for (int s = 0; s < sub_count; ++s)
-    for (int i = 0; i < plen[0]; ++i) { int32_t& v = tabs[static_cast<size_t>(s) * per + i]; v = slot[v]; }
+  for (int s = 0; s < sub_count; ++s) {
+    const int32_t* t = &tabs[static_cast<size_t>(s) * per];
+    for (int i = 0; i < plen[0]; ++i) slotD[t[i]] = 0;
+    for (int i = 0; i < plen[1]; ++i) slotH[t[plen[0] + i]] = 0;
+  }
+  std::vector<int32_t> srcD, srcH;            // slot -> index
+  for (int64_t d = 0; d < S0; ++d) if (slotD[d] == 0) { slotD[d] = static_cast<int32_t>(srcD.size()); srcD.push_back(static_cast<int32_t>(d)); }
+  for (int64_t h = 0; h < S1; ++h) if (slotH[h] == 0) { slotH[h] = static_cast<int32_t>(srcH.size()); srcH.push_back(static_cast<int32_t>(h)); }
+  const int64_t nD = static_cast<int64_t>(srcD.size()), nH = static_cast<int64_t>(srcH.size());
+  const std::vector<int32_t> tabs_src = tabs;                 // un-remapped copy: upload units compare these
+  for (int s = 0; s < sub_count; ++s) {
+    int32_t* t = &tabs[static_cast<size_t>(s) * per];
+    for (int i = 0; i < plen[0]; ++i) t[i] = slotD[t[i]];
+    for (int i = 0; i < plen[1]; ++i) t[plen[0] + i] = slotH[t[plen[0] + i]];
+  }
   // output: the D-range [dlo, dhi) spanned by the owned blocks
   int64_t dlo = S0, dhi = 0;
   for (int s = 0; s < sub_count; ++s) {
@@ -1177,31 +1288,90 @@ int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32
     dlo = std::min<int64_t>(dlo, a0); dhi = std::max<int64_t>(dhi, a0 + crop[0]);
   }
   const int64_t ND = dhi - dlo;
-  // anchors relative to the output slab
   std::vector<int32_t> anchors(add_idx0 + static_cast<size_t>(sub_first) * 3, add_idx0 + static_cast<size_t>(sub_first + sub_count) * 3);
   for (int s = 0; s < sub_count; ++s) anchors[static_cast<size_t>(s) * 3] -= static_cast<int32_t>(dlo);
 
-  const size_t in_bytes = static_cast<size_t>(3) * n_slots * plane_in;
+  const size_t row_in = static_cast<size_t>(S2) * ies;
+  const size_t in_bytes = static_cast<size_t>(3) * nD * nH * row_in;
   const size_t out_bytes = static_cast<size_t>(3) * ND * plane_out;
   if ((rc = ensure(ctx, &ctx->d_box, &ctx->box_cap, in_bytes))) return rc;
-  if ((rc = ensure(ctx, &ctx->d_disp, &ctx->out_cap, out_bytes))) return rc;
-  if (ctx->vel && (rc = ensure(ctx, &ctx->d_velo, &ctx->velo_cap, out_bytes))) return rc;
-  // Whole planes, one copy per channel and run of consecutive planes, on the compute stream.
-  // (A split upload -- the first subbox's H-rows first, the rest on the copy stream -- saved ~8 ms
-  // per call but faulted with "illegal memory access" whenever the plan was rebuilt inside the same
-  // call; not understood, so not shipped.)
-  for (int64_t d0 = 0; d0 < S0;) {                        // runs of consecutive planes = consecutive slots
-    if (slot[d0] < 0) { ++d0; continue; }
-    int64_t d1 = d0;
-    while (d1 < S0 && slot[d1] >= 0) ++d1;
-    for (int c = 0; c < 3; ++c)
-      CK(cudaMemcpyAsync(static_cast<uint8_t*>(ctx->d_box) + (static_cast<size_t>(c) * n_slots + slot[d0]) * plane_in,
-                         static_cast<const uint8_t*>(in_host) + (static_cast<size_t>(c) * S0 + d0) * plane_in,
-                         static_cast<size_t>(d1 - d0) * plane_in, cudaMemcpyHostToDevice, st));
-    d0 = d1;
+  if (!blocks) {
+    if ((rc = ensure(ctx, &ctx->d_disp, &ctx->out_cap, out_bytes))) return rc;
+    if (ctx->vel && (rc = ensure(ctx, &ctx->d_velo, &ctx->velo_cap, out_bytes))) return rc;
+  }
+  // every allocation of this call happens before the first copy is enqueued: the plan (arena, tensor
+  // maps) and the index tables are sized here, not between uploads
+  {
+    Plan* P = nullptr;
+    if ((rc = build_plan(ctx, plen, 1, &P))) return rc;
+    if ((rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_idx), &ctx->idx_cap, static_cast<size_t>(sub_count) * per * sizeof(int32_t)))) return rc;
+  }
+
+  // ---- upload, in the order the subboxes need it, on its own stream.  Consecutive subboxes with the
+  // same D and H tables form a unit; a unit uploads the (plane, row) rectangles no earlier unit has
+  // brought in -- one strided 2-D copy per channel and rectangle -- and records an event the compute
+  // stream waits on before the unit's first subbox.  Only the first unit's window (224 x 224 rows of
+  // the 512^3 box: 5 ms) is exposed; the rest arrives behind the running subboxes.
+  std::vector<cudaEvent_t> up_ev(static_cast<size_t>(sub_count), nullptr);
+  auto destroy_events = [&]() { for (auto e : up_ev) if (e) cudaEventDestroy(e); };
+  {
+    std::vector<uint8_t> have(static_cast<size_t>(nD * nH), 0);
+    typedef std::vector<std::pair<int32_t, int32_t>> Runs;       // (first H slot, count)
+    for (int u0 = 0; u0 < sub_count;) {
+      int u1 = u0;
+      while (u1 + 1 < sub_count && memcmp(&tabs_src[static_cast<size_t>(u1 + 1) * per], &tabs_src[static_cast<size_t>(u0) * per],
+                                         sizeof(int32_t) * (plen[0] + plen[1])) == 0) ++u1;
+      const int32_t* t = &tabs[static_cast<size_t>(u0) * per];
+      std::vector<int32_t> ud(t, t + plen[0]), uh(t + plen[0], t + plen[0] + plen[1]);
+      std::sort(ud.begin(), ud.end()); ud.erase(std::unique(ud.begin(), ud.end()), ud.end());
+      std::sort(uh.begin(), uh.end()); uh.erase(std::unique(uh.begin(), uh.end()), uh.end());
+      auto missing = [&](int32_t d) {
+        Runs r;
+        for (size_t i = 0; i < uh.size();) {
+          if (have[static_cast<size_t>(d) * nH + uh[i]]) { ++i; continue; }
+          size_t j = i;
+          while (j + 1 < uh.size() && uh[j + 1] == uh[j] + 1 && srcH[uh[j + 1]] == srcH[uh[j]] + 1 &&
+                 !have[static_cast<size_t>(d) * nH + uh[j + 1]]) ++j;
+          r.emplace_back(uh[i], static_cast<int32_t>(j - i + 1));
+          i = j + 1;
+        }
+        return r;
+      };
+      bool any = false;
+      for (size_t i = 0; i < ud.size();) {
+        const Runs r0 = missing(ud[i]);
+        size_t j = i;
+        while (j + 1 < ud.size() && ud[j + 1] == ud[j] + 1 && srcD[ud[j + 1]] == srcD[ud[j]] + 1 && missing(ud[j + 1]) == r0) ++j;
+        for (const auto& run : r0) {
+          for (int c = 0; c < 3; ++c) {
+            uint8_t* dst = static_cast<uint8_t*>(ctx->d_box) + ((static_cast<size_t>(c) * nD + ud[i]) * nH + run.first) * row_in;
+            const uint8_t* src = static_cast<const uint8_t*>(in_host) +
+                                 ((static_cast<size_t>(c) * S0 + srcD[ud[i]]) * S1 + srcH[run.first]) * row_in;
+            cudaError_t e = cudaMemcpy2DAsync(dst, static_cast<size_t>(nH) * row_in, src, static_cast<size_t>(S1) * row_in,
+                                              static_cast<size_t>(run.second) * row_in, j - i + 1, cudaMemcpyHostToDevice, us);
+            if (e != cudaSuccess) {
+              cudaStreamSynchronize(us); destroy_events();
+              return fail(ctx, NBE_ERR_CUDA, "process_box upload: %s", cudaGetErrorString(e));
+            }
+          }
+          for (size_t q = i; q <= j; ++q)
+            for (int32_t h = run.first; h < run.first + run.second; ++h) have[static_cast<size_t>(ud[q]) * nH + h] = 1;
+          any = true;
+        }
+        i = j + 1;
+      }
+      if (any) {
+        cudaEventCreateWithFlags(&up_ev[u0], cudaEventDisableTiming);
+        cudaEventRecord(up_ev[u0], us);
+      }
+      u0 = u1 + 1;
+    }
   }
   cudaEvent_t done;
-  CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+  if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess) {
+    cudaStreamSynchronize(us); destroy_events();
+    return fail(ctx, NBE_ERR_CUDA, "cudaEventCreate failed");
+  }
   // Copy-back policy: consecutive subboxes sharing a D anchor form a run; when a run tiles the
   // whole (H, W) plane the finished D-slab is contiguous per channel and goes back as one large
   // copy per channel, otherwise each owned block is pasted with a strided 3-D copy.
@@ -1250,21 +1420,75 @@ int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32
     for (int q = g0; q <= g1; ++q) { group_end[q] = g1; bulk[q] = is_bulk ? 1 : 0; }
     g0 = g1 + 1;
   }
-  const int32_t size_in[3] = {static_cast<int32_t>(n_slots), size[1], size[2]};
+  const int32_t size_in[3] = {static_cast<int32_t>(nD), static_cast<int32_t>(nH), size[2]};
   const int32_t size_out[3] = {static_cast<int32_t>(ND), size[1], size[2]};
   rc = process_box_core(ctx, ctx->d_box, in_dtype, size_in, size_out, crop, plen, tabs.data(), anchors.data(), 0, sub_count,
-                        Dz, vel_fac, ctx->d_disp, ctx->d_velo, out_dtype, st, [&](int s) -> int {
+                        Dz, vel_fac, blocks ? disp_blk : ctx->d_disp, blocks ? vel_blk : ctx->d_velo, out_dtype, st,
+                        [&](int s) -> int {
+                          // before subbox s + 1 may start, its unit's upload must have landed
+                          if (s + 1 < sub_count && up_ev[s + 1]) CK(cudaStreamWaitEvent(st, up_ev[s + 1], 0));
+                          if (blocks) return NBE_OK;
                           // full (H, W)-tiling runs go back as one contiguous copy per channel when they end;
                           // everything else -- partial runs (sharded ranges) and the last run, whose copy
                           // nothing would hide -- is pasted subbox by subbox behind the next subbox's compute
                           return (!bulk[s] || s == group_end[s]) ? flush_run(s) : NBE_OK;
-                        });
-  cudaError_t e1 = cudaStreamSynchronize(st);      // also on error paths: the caller's buffers must be quiescent
+                        }, blocks, up_ev[0]);
+  cudaError_t e0 = cudaStreamSynchronize(us);      // also on error paths: the caller's buffers must be quiescent
+  cudaError_t e1 = cudaStreamSynchronize(st);
   cudaError_t e2 = cudaStreamSynchronize(cs);
   cudaEventDestroy(done);
+  destroy_events();
   if (rc) return rc;
+  if (e0 != cudaSuccess) return fail(ctx, NBE_ERR_CUDA, "process_box upload: %s", cudaGetErrorString(e0));
   if (e1 != cudaSuccess) return fail(ctx, NBE_ERR_CUDA, "process_box: %s", cudaGetErrorString(e1));
   if (e2 != cudaSuccess) return fail(ctx, NBE_ERR_CUDA, "process_box copy: %s", cudaGetErrorString(e2));
+  return NBE_OK;
+}
+
+int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32_t size[3], const int32_t crop[3],
+                    const int32_t plen[3], const int32_t* crop_idx, const int32_t* add_idx0, int sub_first,
+                    int sub_count, float Dz, float vel_fac, void* disp_host, void* vel_host, int out_dtype) {
+  if (!ctx) return NBE_ERR_ARG;
+  return process_box_host(ctx, in_host, in_dtype, size, crop, plen, crop_idx, add_idx0, sub_first, sub_count, Dz, vel_fac,
+                          disp_host, vel_host, out_dtype, nullptr, nullptr);
+}
+
+int nbe_process_box_blocks(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32_t size[3], const int32_t crop[3],
+                           const int32_t plen[3], const int32_t* crop_idx, const int32_t* add_idx0, int sub_first,
+                           int sub_count, float Dz, float vel_fac, void* disp_blocks_dev, void* vel_blocks_dev, int out_dtype) {
+  if (!ctx) return NBE_ERR_ARG;
+  if (!disp_blocks_dev) return fail(ctx, NBE_ERR_ARG, "null argument");
+  return process_box_host(ctx, in_host, in_dtype, size, crop, plen, crop_idx, add_idx0, sub_first, sub_count, Dz, vel_fac,
+                          nullptr, nullptr, out_dtype, disp_blocks_dev, vel_blocks_dev);
+}
+
+// One call, all GPUs: the subbox range is cut into contiguous shares (the first n % ngpu contexts get
+// one more), one host thread per context runs nbe_process_box on its share.  Every GPU reads its
+// window from the SAME page-locked input and DMAs its finished blocks into the SAME output arrays:
+// the shares are disjoint, so there is no exchange step and no per-GPU copy of the box on the host.
+int nbe_process_box_multi(nbe_ctx** ctxs, int ngpu, const void* in_host, int in_dtype, const int32_t size[3],
+                          const int32_t crop[3], const int32_t plen[3], const int32_t* crop_idx, const int32_t* add_idx0,
+                          int sub_first, int sub_count, float Dz, float vel_fac, void* disp_host, void* vel_host,
+                          int out_dtype) {
+  if (!ctxs || ngpu < 1) return NBE_ERR_ARG;
+  for (int g = 0; g < ngpu; ++g) if (!ctxs[g]) return NBE_ERR_ARG;
+  if (sub_count < 0) return fail(ctxs[0], NBE_ERR_ARG, "sub_count < 0");
+  std::vector<int> rcs(static_cast<size_t>(ngpu), NBE_OK);
+  std::vector<std::thread> th;
+  const int base = sub_count / ngpu, rem = sub_count % ngpu;
+  for (int g = 0; g < ngpu; ++g) {
+    const int lo = g * base + std::min(g, rem), cnt = base + (g < rem ? 1 : 0);
+    th.emplace_back([=, &rcs]() {
+      rcs[g] = process_box_host(ctxs[g], in_host, in_dtype, size, crop, plen, crop_idx, add_idx0, sub_first + lo, cnt, Dz,
+                                vel_fac, disp_host, vel_host, out_dtype, nullptr, nullptr);
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int g = 0; g < ngpu; ++g)
+    if (rcs[g]) {
+      if (g != 0) ctxs[0]->err = "gpu " + std::to_string(ctxs[g]->device) + ": " + ctxs[g]->err;
+      return rcs[g];
+    }
   return NBE_OK;
 }
 
@@ -1273,11 +1497,12 @@ int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32
 // page-locked (nothing to undo), negative on error.  Never leaves a sticky CUDA error behind.
 int nbe_host_register(nbe_ctx* ctx, void* ptr, size_t bytes) {
   if (!ctx || !ptr) return NBE_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  ENTER_DEVICE(ctx);
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeHost) return 0;
   cudaGetLastError();
-  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+  // portable: every GPU of the process DMAs from / into the same buffer (nbe_process_box_multi)
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
   if (e == cudaSuccess) return 1;
   cudaGetLastError();
   if (e == cudaErrorHostMemoryAlreadyRegistered) return 0;
@@ -1286,7 +1511,7 @@ int nbe_host_register(nbe_ctx* ctx, void* ptr, size_t bytes) {
 
 int nbe_host_unregister(nbe_ctx* ctx, void* ptr) {
   if (!ctx || !ptr) return NBE_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  ENTER_DEVICE(ctx);
   cudaError_t e = cudaHostUnregister(ptr);
   cudaGetLastError();
   return e == cudaSuccess ? NBE_OK : NBE_ERR_CUDA;
@@ -1298,7 +1523,7 @@ int nbe_density_from_psi(nbe_ctx* ctx, const float* psi_dev, const int32_t n[3],
   if (!psi_dev || !delta_dev || !n || n[0] < 1 || n[1] < 1 || n[2] < 1 || res < 1 || !(boxsize > 0.f))
     return fail(ctx, NBE_ERR_ARG, "nbe_density_from_psi: bad argument");
   if (worder < 1 || worder > 4) return fail(ctx, NBE_ERR_ARG, "Unsupported mass-assignment order: %d", worder);
-  CK(cudaSetDevice(ctx->device));
+  ENTER_DEVICE(ctx);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long cells = 1ll * res * res * res, np = 1ll * n[0] * n[1] * n[2];
   CK(cudaMemsetAsync(delta_dev, 0, cells * sizeof(float), st));
@@ -1320,7 +1545,7 @@ int nbe_density_from_psi(nbe_ctx* ctx, const float* psi_dev, const int32_t n[3],
 int nbe_mas_deconvolve(nbe_ctx* ctx, void* delta_k_dev, int32_t res, int32_t worder, void* stream) {
   if (!ctx) return NBE_ERR_ARG;
   if (!delta_k_dev || res < 1 || worder < 1 || worder > 4) return fail(ctx, NBE_ERR_ARG, "nbe_mas_deconvolve: bad argument");
-  CK(cudaSetDevice(ctx->device));
+  ENTER_DEVICE(ctx);
   const long long n = 1ll * res * res * (res / 2 + 1);
   const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 32ll * ctx->num_sms));
   mas_deconvolve_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<float2*>(delta_k_dev), res, worder);
@@ -1334,7 +1559,7 @@ int nbe_pk_bins(nbe_ctx* ctx, const void* delta_k_dev, int32_t res, int32_t mas_
   if (!ctx) return NBE_ERR_ARG;
   if (!delta_k_dev || !out_dev || res < 1 || mas_order < 0 || mas_order > 4 || nbins < 1 || nbins > kPkMaxBins)
     return fail(ctx, NBE_ERR_ARG, "nbe_pk_bins: bad argument");
-  CK(cudaSetDevice(ctx->device));
+  ENTER_DEVICE(ctx);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CK(cudaMemsetAsync(out_dev, 0, 3 * sizeof(double) * nbins, st));
   const long long n = 1ll * res * res * (res / 2 + 1);
@@ -1350,7 +1575,7 @@ int nbe_pk_bins(nbe_ctx* ctx, const void* delta_k_dev, int32_t res, int32_t mas_
 int nbe_za_psi_k(nbe_ctx* ctx, const void* delta_k_dev, int32_t res, float boxsize, void* psi_k_dev, void* stream) {
   if (!ctx) return NBE_ERR_ARG;
   if (!delta_k_dev || !psi_k_dev || res < 1 || !(boxsize > 0.f)) return fail(ctx, NBE_ERR_ARG, "nbe_za_psi_k: bad argument");
-  CK(cudaSetDevice(ctx->device));
+  ENTER_DEVICE(ctx);
   const long long n = 1ll * res * res * (res / 2 + 1);
   const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 32ll * ctx->num_sms));
   za_psi_k_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -1369,7 +1594,7 @@ int64_t nbe_launch_count(nbe_ctx* ctx, int reset) {
 
 int nbe_set_profiling(nbe_ctx* ctx, int enable) {
   if (!ctx) return NBE_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  ENTER_DEVICE(ctx);
   resolve_profile(ctx);
   ctx->profiling = enable != 0;
   if (enable) {     // start a fresh accumulation
@@ -1381,7 +1606,7 @@ int nbe_set_profiling(nbe_ctx* ctx, int enable) {
 
 int nbe_get_profile(nbe_ctx* ctx, int cap, const char** names, float* ms, double* flops) {
   if (!ctx) return NBE_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  ENTER_DEVICE(ctx);
   resolve_profile(ctx);
   const int n = static_cast<int>(ctx->prof_names.size());
   for (int i = 0; i < n && i < cap; ++i) {
@@ -1396,7 +1621,7 @@ int nbe_get_profile(nbe_ctx* ctx, int cap, const char** names, float* ms, double
 // which: 0 = hi, 1 = lo, 2 = tangent.  shape_out = {d, h, w, c}.  Returns bytes copied or <0.
 long long nbe_debug_read_act(nbe_ctx* ctx, int act, int which, void* host, size_t cap, int32_t shape_out[4]) {
   if (!ctx || ctx->plans.empty() || act < 0 || act >= A_OUT) return NBE_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  DevGuard dev_guard_(ctx->device);
   cudaDeviceSynchronize();
   Plan* P = ctx->plans.back();
   const ActBuf& B = P->act[act];

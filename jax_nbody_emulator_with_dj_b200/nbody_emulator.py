@@ -67,29 +67,54 @@ def _astype(x, dtype):
     return np.asarray(x).astype(dtype)
 
 
-def load_default_parameters() -> dict:
-    """Load the pretrained parameters shipped with the package
-    (model_parameters/nbody_emulator_params.npz, a pickled {'block': {'layer': {...}}} tree)."""
-    params_path = Path(__file__).parent / "model_parameters" / "nbody_emulator_params.npz"
+PARAMS_ENV = "NBE_PARAMS"
+DEFAULT_PARAMS_PATH = Path(__file__).parent / "model_parameters" / "nbody_emulator_params.npz"
+
+
+def load_default_parameters(path=None) -> dict:
+    """Load the pretrained parameters (reference: nbody_emulator.py:115-129).
+
+    The file is the reference's ``nbody_emulator_params.npz``: one pickled object array ``params``
+    holding the tree ``{block: {layer: {weight, bias, style_weight, style_bias}}}``.  Looked up in
+    this order: the ``path`` argument, the ``NBE_PARAMS`` environment variable, then
+    ``model_parameters/nbody_emulator_params.npz`` inside this package (the reference's location;
+    the blob itself is not redistributed with either checkout)."""
+    import os
+    params_path = Path(path) if path is not None else Path(os.environ.get(PARAMS_ENV) or DEFAULT_PARAMS_PATH)
+    if not params_path.exists():
+        raise FileNotFoundError(
+            f"{params_path} not found: copy the reference package's model_parameters/nbody_emulator_params.npz "
+            f"there, or point {PARAMS_ENV} (or the path argument) at it")
     with np.load(params_path, allow_pickle=True) as f:
         params = f['params'].item()
     return {'params': params}
 
 
 def _modulate_tree(params, z, Om, vel, eps):
+    """Both premodulation entry points: the math runs in the fused CUDA modulation kernel for all 33
+    layers at once and is read back as fp32.  Like the reference (nbody_emulator.py:166-185, :238-264)
+    the decision is per layer: layers with ``style_weight`` are modulated, anything else is passed
+    through with a 'skipping' note.  The kernel needs the complete styled net, so a tree in which only
+    some of the 33 conv layers carry style parameters is rejected instead of being silently returned
+    un-modulated."""
     Dz = np.float32(growth_factor(z, Om))
-    eng = Engine.get()
-    has_style = all('style_weight' in params['params'][b][l] for b, l, *_ in LAYERS
-                    if b in params['params'] and l in params['params'][b])
-    out = {'params': {}}
-    if has_style:
+    P = params['params']
+    idx = {(b, l): i for i, (b, l, *_r) in enumerate(LAYERS)}
+    styled = [(b, l) for (b, l) in idx if b in P and l in P[b] and 'style_weight' in P[b][l]]
+    eng = None
+    if styled:
+        if len(styled) != len(idx):
+            missing = sorted(set(idx) - set(styled))
+            raise ValueError(f"cannot modulate a partially styled tree: {len(missing)} of the 33 conv layers have no "
+                             f"'style_weight' (first: {missing[0][0]}/{missing[0][1]})")
+        eng = Engine.get()
         eng.set_params(params, False, vel, eps)
         eng.modulate(np.float32(Om), Dz)
-    idx = {(b, l): i for i, (b, l, *_r) in enumerate(LAYERS)}
-    for bname, bp in params['params'].items():
+    out = {'params': {}}
+    for bname, bp in P.items():
         out['params'][bname] = {}
         for lname, lp in bp.items():
-            if 'style_weight' in lp and has_style and (bname, lname) in idx:
+            if eng is not None and 'style_weight' in lp and (bname, lname) in idx:
                 w, dw = eng.get_modulated(idx[(bname, lname)], 0, want_dw=vel)
                 ent = {'weight': w, 'bias': lp['bias']}
                 if vel:
@@ -98,7 +123,8 @@ def _modulate_tree(params, z, Om, vel, eps):
             else:
                 print(f'skipping {bname} {lname}')
                 out['params'][bname][lname] = lp
-    eng.invalidate()
+    if eng is not None:
+        eng.invalidate()
     return out
 
 
@@ -116,7 +142,9 @@ def modulate_emulator_parameters_vel(params, z, Om, eps=1.e-8):
 def create_emulator(premodulate: bool = False, compute_vel: bool = True, load_params: bool = True,
                     processor_config: SubboxConfig | None = None, premodulate_z: float | None = None,
                     premodulate_Om: float | None = None, dtype=None, **model_kwargs) -> NBodyEmulator:
-    """Factory: model (+ params, + processor).  Same arguments and errors as the reference."""
+    """Factory: model (+ params, + processor).  Same arguments and errors as the reference.
+    Extra keyword (not in the reference): ``params_path`` -- file for load_default_parameters."""
+    params_path = model_kwargs.pop("params_path", None)
     from .models import (NBodyEmulatorCore, NBodyEmulatorVelCore, StyleNBodyEmulatorCore,
                          StyleNBodyEmulatorVelCore)
     precision = model_kwargs.pop("precision", None)
@@ -129,7 +157,7 @@ def create_emulator(premodulate: bool = False, compute_vel: bool = True, load_pa
 
     params = None
     if load_params:
-        params = load_default_parameters()
+        params = load_default_parameters(params_path)
         if premodulate:
             if premodulate_z is None or premodulate_Om is None:
                 raise ValueError("premodulate_z and premodulate_Om are required "

@@ -90,6 +90,36 @@ def _pinned_zeros(shape, np_dtype):
     return t, t.numpy()
 
 
+class _OutputPool:
+    """Page-locked output boxes, handed to the caller WITHOUT a copy and never written again while the
+    caller (or any view of the array) is alive.
+
+    Every GPU DMAs its finished blocks straight into the array ``process_box`` returns.  Page-locking a
+    multi-GB buffer costs about as much as a whole 8-GPU box, so buffers are recycled -- but only once
+    the array handed out has been garbage-collected (tracked with a weak reference; views keep their
+    base alive).  A caller who keeps every result therefore gets a fresh buffer per call (the
+    reference's semantics: outputs are freshly allocated, subbox.py:168-170); a caller who drops or
+    overwrites the previous result before the next call reuses the same pinned memory at no cost."""
+
+    def __init__(self):
+        self.entries = []      # [key, tensor, weakref-to-array | None, owned range]
+
+    def take(self, key, shape, np_dtype, own_range):
+        import weakref
+        for e in self.entries:
+            if e[0] == key and (e[2] is None or e[2]() is None):
+                arr = e[1].numpy()
+                if e[3] != own_range:      # voxels outside the owned range must read zero
+                    arr.fill(0)
+                e[2], e[3] = weakref.ref(arr), own_range
+                return arr
+        t, arr = _pinned_zeros(shape, np_dtype)
+        self.entries.append([key, t, weakref.ref(arr), own_range])
+        # drop recyclable buffers of other shapes / dtypes
+        self.entries = [e for e in self.entries if e[0] == key or (e[2] is not None and e[2]() is not None)]
+        return arr
+
+
 class SubboxProcessor:
     """Unified subbox processor for all four model variants (subbox.py:99-137)."""
 
@@ -109,9 +139,9 @@ class SubboxProcessor:
         elif t in (NBodyEmulatorCore, StyleNBodyEmulatorCore):
             self.compute_vel = False
         self._tables = None
-        self._out = None           # cached pinned output buffers
-        self._out_range = None
-        self._pinned_in = None     # (ptr, nbytes) of the host input currently page-locked
+        self._pool = _OutputPool()
+        self._pinned_in = None     # (key, array, registered-by-us) of the host input currently page-locked
+        self.last_gather = None    # {"bytes", "ms", "GBps"} of the most recent NCCL output gather
 
     def close(self):
         """Release the page-lock on the cached input buffer (also called on garbage collection: a
@@ -127,15 +157,6 @@ class SubboxProcessor:
 
     def __del__(self):
         self.close()
-
-    def _outputs(self, shape, out_np):
-        key = (shape, np.dtype(out_np).name, self.compute_vel)
-        if self._out is None or self._out[0] != key:
-            dis = _pinned_zeros(shape, out_np)
-            vel = _pinned_zeros(shape, out_np) if self.compute_vel else (None, None)
-            self._out = (key, dis, vel)
-            self._out_range = None
-        return self._out[1][1], self._out[2][1]
 
     def _pin_input(self, eng, box):
         """Page-lock the caller's array in place so that the upload is a single asynchronous DMA;
@@ -170,21 +191,45 @@ class SubboxProcessor:
             self._merged = (key, m, m.flat_tables())
         return self._merged[1], self._merged[2]
 
-    def process_box(self, input_box, z, Om, desc="Processing subboxes", show_progress=True,
-                    shard=None, gather="all", copy=True, merge=None, out=None):
-        """Process the whole box; returns displacement (C,D,H,W) or (displacement, velocity) as
-        numpy arrays of ``config.output_dtype``.
+    def _engines(self, devices, dist):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            Engine.get()                      # raises the "no CPU fallback" error
+        if devices is None or devices == "all":
+            if dist is not None and dist.get_world_size() > 1:
+                devices = [torch.cuda.current_device()]       # one process per GPU: this rank's device
+            else:
+                devices = list(range(torch.cuda.device_count()))
+        elif isinstance(devices, int):
+            devices = [devices]
+        devices = [int(d) for d in devices]
+        if not devices or len(set(devices)) != len(devices):
+            raise ValueError(f"devices must be distinct CUDA device indices, got {devices}")
+        return [Engine.get(d) for d in devices]
 
+    def process_box(self, input_box, z, Om, desc="Processing subboxes", show_progress=True,
+                    shard=None, gather="all", copy=None, merge=None, out=None, devices=None):
+        """Process the whole box; returns displacement (C,D,H,W) or (displacement, velocity) as
+        numpy arrays of ``config.output_dtype`` (reference signature: subbox.py:139-147).
+
+        devices: CUDA devices this call drives.  None (default) = every visible GPU when the process is
+        alone, this rank's current device under ``torch.distributed`` (one process per GPU).  With
+        several devices the subboxes are cut into contiguous shares, one host thread per GPU
+        (``nbe_process_box_multi``): all GPUs read their (D, H) window from the one page-locked input
+        and write their finished blocks into the one output box -- nothing is duplicated on the host.
+        Returned arrays: page-locked memory the GPUs wrote directly; they belong to the caller and are
+        never touched again while referenced (``_OutputPool``); ``copy=True`` forces an ordinary
+        pageable numpy copy instead.
         shard: None = shard over torch.distributed ranks iff initialised with world_size > 1;
         (rank, world) forces a split (each rank returns only its own voxels, rest zero) unless
-        ``gather`` is "all" (all-gather over NCCL/gloo) or "rank0".
-        copy: True returns fresh arrays (reference semantics); False returns views of the
-        processor's pinned output buffers, valid until the next call (saves a host memcpy).
+        ``gather`` is "all" / "rank0": then the blocks are all-gathered on the DEVICES over NCCL
+        (NVLink), re-assembled there and copied to the host once (gloo / CPU tensors in the tests: a
+        sum of the disjoint boxes).  With gather="rank0" only rank 0 returns arrays (others: None).
         merge: e.g. (2, 2, 1) processes 2x2x1 reference subboxes as one larger tile (bit-identical
         output, fewer halo FLOPs, more activation memory).
         out: (disp, vel) or disp -- caller-provided C-contiguous arrays of shape (C,)+size and
         output_dtype (e.g. np.memmap for boxes that do not fit in RAM; input_box may be a memmap
-        too).  Only the voxels owned by this rank's subboxes are written; nothing is zeroed.
+        too).  Only the voxels owned by this call's subboxes are written; nothing is zeroed.
         """
         cfg = self.config
         tables = None
@@ -210,17 +255,28 @@ class SubboxProcessor:
         rank, world = shard
         lo, hi = shard_range(n, rank, world)
 
-        eng = Engine.get()
-        eng.set_precision(self.model.precision)
-        eng.set_params(self.params, self.premodulate, self.compute_vel, self.model.eps)
-        eng.modulate(None if self.premodulate else np.float32(Om), Dz)
+        engines = self._engines(devices, dist)
+        for eng in engines:
+            eng.set_precision(self.model.precision)
+            eng.set_params(self.params, self.premodulate, self.compute_vel, self.model.eps)
+            eng.modulate(None if self.premodulate else np.float32(Om), Dz)
+        eng = engines[0]
         if tables is None:
             if self._tables is None:
                 self._tables = cfg.flat_tables()
             tables = self._tables
         crop_idx, add0, plen = tables
-
         shape = (cfg.in_chan,) + tuple(cfg.size)
+        self._pin_input(eng, box)
+
+        nccl_gather = (world > 1 and dist is not None and gather in ("all", "rank0") and out is None
+                       and dist.get_backend() == "nccl")
+        if nccl_gather:
+            if len(engines) != 1:
+                raise ValueError("the NCCL output gather runs one process per GPU: pass a single device")
+            return self._process_gather_nccl(dist, cfg, eng, box, in_np, out_np, plen, crop_idx, add0, lo, hi, n, rank,
+                                             world, Dz, vf, gather, copy)
+
         if out is not None:
             outs = out if isinstance(out, (tuple, list)) else (out,)
             if len(outs) != (2 if self.compute_vel else 1):
@@ -228,25 +284,24 @@ class SubboxProcessor:
             for a in outs:
                 if a.shape != shape or a.dtype != out_np or not a.flags["C_CONTIGUOUS"]:
                     raise ValueError(f"out arrays must be C-contiguous {shape} of {out_np}")
+            if world > 1 and dist is not None and gather in ("all", "rank0"):
+                raise ValueError("out= receives only this rank's voxels: use gather='none' with out=")
             dis, vel = outs[0], (outs[1] if self.compute_vel else None)
             copy = False
         else:
-            dis, vel = self._outputs(shape, out_np)
-            # voxels not owned by [lo, hi) must read zero: the cached buffers only need clearing when
-            # the owned range differs from the previous call's (owned blocks are always overwritten)
-            if self._out_range not in (None, (lo, hi)):
-                dis.fill(0)
-                if vel is not None:
-                    vel.fill(0)
-            self._out_range = (lo, hi)
-        self._pin_input(eng, box)
+            dis = self._pool.take(("d", shape, out_np.name), shape, out_np, (lo, hi))
+            vel = self._pool.take(("v", shape, out_np.name), shape, out_np, (lo, hi)) if self.compute_vel else None
         bar = None
         if show_progress:
             from tqdm import tqdm
             bar = tqdm(total=hi - lo, desc=desc, ncols=80,
                        bar_format='{desc}: {percentage:3.0f}%|{bar:30}| {n_fmt}/{total_fmt} [{elapsed}<{remaining}]')
-        eng.process_box(box, dtype_code(in_np), cfg.size, cfg.crop_size, plen, crop_idx, add0, lo, hi - lo,
-                        Dz, vf, dis, vel, dtype_code(out_np))
+        args = (box, dtype_code(in_np), cfg.size, cfg.crop_size, plen, crop_idx, add0, lo, hi - lo, Dz, vf, dis, vel,
+                dtype_code(out_np))
+        if len(engines) > 1:
+            Engine.process_box_multi(engines, *args)
+        else:
+            eng.process_box(*args)
         if bar is not None:
             bar.update(hi - lo)
             bar.close()
@@ -259,10 +314,65 @@ class SubboxProcessor:
             return dis, vel
         return dis
 
+    def _process_gather_nccl(self, dist, cfg, eng, box, in_np, out_np, plen, crop_idx, add0, lo, hi, n, rank, world,
+                             Dz, vf, gather, copy):
+        """One process per GPU: this rank's subboxes stay on its GPU as (count, 3, c0, c1, c2) records,
+        ncclAllGather moves every record once over NVLink, the box is re-assembled on the device by a
+        strided copy and goes to the host in one DMA."""
+        torch = _torch()
+        dev = torch.device("cuda", eng.device)
+        tdt = {"float32": torch.float32, "float16": torch.float16}[out_np.name]
+        c = tuple(int(v) for v in cfg.crop_size)
+        nd = tuple(int(v) for v in cfg.ndiv)
+        n_max = -(-n // world)
+        rec = (3,) + c
+        nf = 2 if self.compute_vel else 1
+        # [field][rank-local record]: one send buffer for both fields => a single collective
+        send = torch.empty((nf, n_max) + rec, dtype=tdt, device=dev)
+        if hi - lo < n_max:
+            send[:, hi - lo:].zero_()
+        eng.process_box_blocks(box, dtype_code(in_np), cfg.size, cfg.crop_size, plen, crop_idx, add0, lo, hi - lo, Dz, vf,
+                               send[0], send[1] if self.compute_vel else None, dtype_code(out_np))
+        recv = torch.empty((world, nf, n_max) + rec, dtype=tdt, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_gather_into_tensor(recv.view(-1), send.view(-1))
+        e1.record()
+        outs = [None, None]
+        if gather == "all" or rank == 0:
+            shape = (cfg.in_chan,) + tuple(cfg.size)
+            for f in range(nf):
+                if n % world == 0:
+                    blocks = recv[:, f].reshape((n,) + rec)
+                else:
+                    blocks = torch.cat([recv[r, f, :shard_range(n, r, world)[1] - shard_range(n, r, world)[0]]
+                                        for r in range(world)])
+                full = blocks.view(nd + rec).permute(3, 0, 4, 1, 5, 2, 6).reshape(3, nd[0] * c[0], nd[1] * c[1], nd[2] * c[2])
+                host = self._pool.take(("d" if f == 0 else "v", shape, out_np.name), shape, out_np, (0, n))
+                ht = torch.from_numpy(host)
+                if tuple(full.shape) == shape:
+                    ht.copy_(full, non_blocking=True)
+                else:        # remainder strips of a non-divisible box stay zero (SURVEY App. C.1)
+                    ht[:, :full.shape[1], :full.shape[2], :full.shape[3]].copy_(full)
+                outs[f] = host
+            torch.cuda.synchronize(dev)
+            if copy:
+                outs = [np.array(a) if a is not None else None for a in outs]
+        else:
+            torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        nbytes = recv.numel() * recv.element_size()
+        self.last_gather = {"bytes": int(nbytes), "ms": float(ms), "GBps": nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                            "collective": "ncclAllGather of (subbox, 3, c0, c1, c2) records, device to device"}
+        if self.compute_vel:
+            return outs[0], outs[1]
+        return outs[0]
+
 
 def _gather_outputs(dist, cfg, dis, vel, world, mode):
-    """Sum the disjoint per-rank outputs (each voxel is owned by exactly one rank; the others
-    hold zeros).  NCCL over NVLink on GPUs, gloo on CPU tensors in the tests."""
+    """Host / gloo fallback of the output gather (CPU tests; NCCL runs _process_gather_nccl): sum the
+    disjoint per-rank outputs -- each voxel is owned by exactly one rank, the others hold zeros.  The
+    reduction runs on a private copy, so the caller's (possibly cached) arrays are never clobbered."""
     torch = _torch()
     on_gpu = dist.get_backend() == "nccl"
     outs = []
@@ -270,7 +380,7 @@ def _gather_outputs(dist, cfg, dis, vel, world, mode):
         if a is None:
             outs.append(None)
             continue
-        t = torch.from_numpy(a)
+        t = torch.from_numpy(a).clone()
         if on_gpu:
             t = t.cuda()
         if mode == "all":

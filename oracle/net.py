@@ -142,6 +142,10 @@ class Net:
         # ('xp','wp'), how x / W / dW / dx enter the two tangent convs ('xt','wt','dw','dx')
         ident = lambda t: t
         self.ops = {k: (ops or {}).get(k, ident) for k in ("xp", "wp", "xt", "wt", "dw", "dx")}
+        # numerics study only: per-block overrides of `ops` ({block name: ops dict}); the block being
+        # evaluated is tracked in cur_block by forward()
+        self.ops_by_block = {}
+        self.cur_block = None
         self.cap = None          # optional dict: name -> (x, dx) of every stored activation
 
     # ---- one conv layer, primal + tangent  (style_layers_vel.py:108-147) ----
@@ -163,7 +167,7 @@ class Net:
         for i in range(B):
             j = i if per_sample else 0
             xi = x[i:i + 1]
-            o = self.ops
+            o = self.ops_by_block.get(self.cur_block, self.ops)
             ys.append(f(o["xp"](xi), o["wp"](wn[j]), bias))
             if self.vel:
                 dy = f(o["xt"](xi), o["dw"](dwn[j]), None)
@@ -253,6 +257,7 @@ class Net:
 
         def run(name, x, dx):
             kind, seq = blk[name]
+            self.cur_block = name
             if kind == "res":
                 r = self.res_block(P[name], seq, x, dx, s, name)
             else:

@@ -31,9 +31,12 @@ def _worker(rank, world, port, q):
         ai = cfg.all_add_inds[idx]
         dis[ai] = box[ai] * 2
         vel[ai] = box[ai] - 1
-    d_all, v_all = _gather_outputs(dist, cfg, dis.copy(), vel.copy(), world, "all")
-    d0, v0 = _gather_outputs(dist, cfg, dis.copy(), vel.copy(), world, "rank0")
+    keep_d, keep_v = dis.copy(), vel.copy()
+    d_all, v_all = _gather_outputs(dist, cfg, dis, vel, world, "all")
+    d0, v0 = _gather_outputs(dist, cfg, dis, vel, world, "rank0")
     ok = np.array_equal(d_all, box * 2) and np.array_equal(v_all, box - 1)
+    # the reduction never writes into the caller's arrays (they may be the processor's cached buffers)
+    ok = ok and np.array_equal(dis, keep_d) and np.array_equal(vel, keep_v)
     if rank == 0:
         ok = ok and np.array_equal(d0, box * 2) and np.array_equal(v0, box - 1)
     own = np.zeros(size, bool)

@@ -156,3 +156,86 @@ def test_public_names():                    # __init__.py:73-95
               "growth_rate", "dlogH_dloga", "vel_norm", "acc_norm", "StyleNBodyEmulatorCore",
               "StyleNBodyEmulatorVelCore", "NBodyEmulatorCore", "NBodyEmulatorVelCore"]:
         assert hasattr(nb, n) and n in nb.__all__
+
+
+def test_load_default_parameters_reads_the_reference_file_format(tmp_path, monkeypatch):
+    """nbody_emulator.py:115-129: the weights ship as ONE pickled object array 'params' holding
+    {block: {layer: {weight, bias, style_weight, style_bias}}}.  The blob is absent from the reference
+    checkout, so the round trip is exercised on a synthetic file written in exactly that format."""
+    tree = nb.init_params(7)["params"]
+    f = tmp_path / "nbody_emulator_params.npz"
+    np.savez(f, params=np.array(tree, dtype=object))
+    got = nb.load_default_parameters(f)
+    assert set(got) == {"params"} and list(got["params"]) == list(tree)
+    for b, l, co, ci, k in LAYERS:
+        for key, shape in (("weight", (co, ci, k, k, k)), ("bias", (co,)), ("style_weight", (ci, 2)), ("style_bias", (ci,))):
+            assert got["params"][b][l][key].shape == shape
+            assert np.array_equal(got["params"][b][l][key], tree[b][l][key])
+    flatten_params(got, False, True)                      # the tree the C ABI accepts
+    # NBE_PARAMS environment override, and create_emulator(load_params=True) through it
+    monkeypatch.setenv("NBE_PARAMS", str(f))
+    assert np.array_equal(nb.load_default_parameters()["params"]["conv_c"]["skip"]["bias"], tree["conv_c"]["skip"]["bias"])
+    emu = nb.create_emulator(load_params=True)
+    assert emu.params is not None and "conv_r01" in emu.params["params"]
+    emu2 = nb.create_emulator(load_params=True, params_path=f, processor_config=nb.SubboxConfig(size=(8, 8, 8), ndiv=(1, 1, 1)))
+    assert emu2.processor.params is emu2.params
+    with pytest.raises(ValueError, match="premodulate_z and premodulate_Om"):
+        nb.create_emulator(premodulate=True, load_params=True)
+    monkeypatch.delenv("NBE_PARAMS")
+    with pytest.raises(FileNotFoundError, match="NBE_PARAMS"):
+        nb.load_default_parameters(tmp_path / "missing.npz")
+
+
+def test_partially_styled_tree_is_rejected_not_passed_through():
+    P = nb.init_params(3)
+    del P["params"]["conv_l1"]["skip"]["style_weight"]
+    with pytest.raises(ValueError, match="partially styled"):
+        nb.modulate_emulator_parameters(P, 0.5, 0.3)
+    # a fully premodulated tree is passed through layer by layer like the reference does (:184, :263)
+    pm = nb.init_params(3, premodulated=True)
+    out = nb.modulate_emulator_parameters_vel(pm, 0.5, 0.3)
+    assert out["params"]["conv_l00"]["conv_0"] is pm["params"]["conv_l00"]["conv_0"]
+
+
+def test_params_fingerprint_sees_replaced_and_overwritten_leaves():
+    from jax_nbody_emulator_with_dj_b200._engine import params_fingerprint
+    P = nb.init_params(5)
+    f0 = params_fingerprint(P)
+    assert f0 == params_fingerprint(P)
+    P["params"]["conv_l2"]["conv_1"]["weight"] = P["params"]["conv_l2"]["conv_1"]["weight"].copy()
+    f1 = params_fingerprint(P)
+    assert f1 != f0                                    # new leaf object
+    P["params"]["down_l1"]["conv_0"]["weight"][...] *= 2.0
+    assert params_fingerprint(P) != f1                 # same object, new contents
+    assert params_fingerprint({"params": {}}) is None
+
+
+def test_output_pool_never_rewrites_an_array_the_caller_still_holds(monkeypatch):
+    """Returned boxes are the page-locked memory the GPUs wrote into; a buffer is recycled only after
+    the caller dropped the array (and every view of it)."""
+    from jax_nbody_emulator_with_dj_b200 import subbox as sb
+    made = []
+
+    def fake_pinned(shape, np_dtype):
+        t = torch.zeros(shape, dtype=torch.float32)
+        made.append(t)
+        return t, t.numpy()
+    monkeypatch.setattr(sb, "_pinned_zeros", fake_pinned)
+    pool = sb._OutputPool()
+    key, shape = ("d", (3, 4, 4, 4), "float32"), (3, 4, 4, 4)
+    a = pool.take(key, shape, np.float32, (0, 8))
+    a[...] = 1.0
+    b = pool.take(key, shape, np.float32, (0, 8))        # `a` is alive: a second buffer
+    assert len(made) == 2 and not np.shares_memory(a, b) and np.all(a == 1.0)
+    view = a[0]
+    del a
+    c = pool.take(key, shape, np.float32, (0, 8))        # a view keeps the first buffer alive
+    assert len(made) == 3
+    del view, b
+    d = pool.take(key, shape, np.float32, (0, 8))        # now one of them is free: recycled, not re-zeroed
+    assert len(made) == 3
+    d[...] = 5.0
+    del d
+    e = pool.take(key, shape, np.float32, (0, 4))        # another owned range: stale voxels are cleared
+    assert len(made) == 3 and np.all(e == 0)
+    assert c is not None
