@@ -116,11 +116,16 @@ int nbe_process_box(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32
  * in_host and copies its finished blocks into the SAME disp_host / vel_host, which should be
  * page-locked (nbe_host_register, or cudaHostAlloc'ed by the caller).  The shares are disjoint: no
  * exchange step, no per-GPU copy of the box in host memory.  Synchronous; returns the first error
- * (message on ctxs[0]).                                                                          */
+ * (message on ctxs[0]).
+ * out_size0: D extent of disp_host / vel_host, 0 = size[0].  The tables are plain gather / paste
+ * indices into whatever arrays are passed, so a box too large for host or device memory is streamed
+ * as D-slabs: in_host holds the crop[0]+96 planes of one slab of subboxes (size[0] = that count, D
+ * tables = 0..size[0]-1), the outputs its crop[0] planes (out_size0 = crop[0], D anchors 0) --
+ * SubboxProcessor.process_box_streamed, BASELINE config 5.                                        */
 int nbe_process_box_multi(nbe_ctx** ctxs, int ngpu, const void* in_host, int in_dtype, const int32_t size[3],
                           const int32_t crop[3], const int32_t plen[3], const int32_t* crop_idx,
                           const int32_t* add_idx0, int sub_first, int sub_count, float Dz, float vel_fac,
-                          void* disp_host, void* vel_host, int out_dtype);
+                          void* disp_host, void* vel_host, int out_dtype, int32_t out_size0);
 
 /* nbe_process_box with the results left ON THE DEVICE in block layout: disp_blocks_dev / vel_blocks_dev
  * are (sub_count, 3, crop0, crop1, crop2) of out_dtype, one contiguous record per subbox in index order.

@@ -269,7 +269,7 @@ class Engine:
 
     @staticmethod
     def process_box_multi(engines, in_host, in_code, size, crop, plen, crop_idx, add_idx0, first, count, Dz, vel_fac,
-                          disp_host, vel_host, out_code):
+                          disp_host, vel_host, out_code, out_size0=0):
         """One call over several GPUs (nbe_process_box_multi): one host thread per engine inside the
         library, one shared pinned input, one shared output."""
         e0 = engines[0]
@@ -280,7 +280,7 @@ class Engine:
             hs, len(engines), C.c_void_p(in_host.ctypes.data), in_code, a3(size), a3(crop), a3(plen),
             crop_idx.ctypes.data_as(ip), add_idx0.ctypes.data_as(ip), int(first), int(count), float(Dz),
             float(vel_fac), C.c_void_p(disp_host.ctypes.data),
-            C.c_void_p(vel_host.ctypes.data) if vel_host is not None else None, out_code))
+            C.c_void_p(vel_host.ctypes.data) if vel_host is not None else None, out_code, int(out_size0)))
 
     def process_box_dev(self, box_dev, size, crop, plen, crop_idx, add_idx0, first, count, Dz, vel_fac,
                         disp_dev, vel_dev):

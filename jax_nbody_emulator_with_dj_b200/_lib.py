@@ -87,7 +87,7 @@ def load():
         lib.nbe_process_box.argtypes = [vp, vp, C.c_int, i32p, i32p, i32p, i32p, i32p, C.c_int, C.c_int,
                                         C.c_float, C.c_float, vp, vp, C.c_int]
         lib.nbe_process_box_multi.argtypes = [C.POINTER(vp), C.c_int, vp, C.c_int, i32p, i32p, i32p, i32p, i32p, C.c_int,
-                                              C.c_int, C.c_float, C.c_float, vp, vp, C.c_int]
+                                              C.c_int, C.c_float, C.c_float, vp, vp, C.c_int, C.c_int32]
         lib.nbe_process_box_blocks.argtypes = lib.nbe_process_box.argtypes
         lib.nbe_process_box_dev.argtypes = [vp, vp, C.c_int, i32p, i32p, i32p, i32p, i32p, C.c_int, C.c_int,
                                             C.c_float, C.c_float, vp, vp, C.c_int, vp]

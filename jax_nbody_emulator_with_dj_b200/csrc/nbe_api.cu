@@ -969,7 +969,7 @@ int check_box_args(nbe_ctx* ctx, const void* in, const int32_t* size, const int3
 // The gather tables and paste anchors index host and device memory: reject anything out of range
 // before a copy or a launch is enqueued (O(n_sub * plen), negligible).
 int check_tables(nbe_ctx* ctx, const int32_t* size, const int32_t* crop, const int32_t* plen, const int32_t* crop_idx,
-                 const int32_t* add_idx0, int sub_first, int sub_count) {
+                 const int32_t* add_idx0, int sub_first, int sub_count, int64_t out_S0) {
   if (sub_first < 0) return fail(ctx, NBE_ERR_ARG, "sub_first < 0");
   const int per = plen[0] + plen[1] + plen[2];
   for (int s = sub_first; s < sub_first + sub_count; ++s) {
@@ -979,7 +979,7 @@ int check_tables(nbe_ctx* ctx, const int32_t* size, const int32_t* crop, const i
         if (t[i] < 0 || t[i] >= size[d]) return fail(ctx, NBE_ERR_ARG, "crop_idx of subbox %d, dim %d out of range: %d", s, d, t[i]);
       t += plen[d];
       const int32_t a = add_idx0[static_cast<size_t>(s) * 3 + d];
-      if (a < 0 || a + crop[d] > size[d]) return fail(ctx, NBE_ERR_ARG, "add_idx0 of subbox %d, dim %d out of range: %d", s, d, a);
+      if (a < 0 || a + crop[d] > (d == 0 ? out_S0 : size[d])) return fail(ctx, NBE_ERR_ARG, "add_idx0 of subbox %d, dim %d out of range: %d", s, d, a);
     }
   }
   return NBE_OK;
@@ -1244,13 +1244,14 @@ int nbe_process_box_dev(nbe_ctx* ctx, const void* box_dev, int in_dtype, const i
 static int process_box_host(nbe_ctx* ctx, const void* in_host, int in_dtype, const int32_t size[3], const int32_t crop[3],
                             const int32_t plen[3], const int32_t* crop_idx, const int32_t* add_idx0, int sub_first,
                             int sub_count, float Dz, float vel_fac, void* disp_host, void* vel_host, int out_dtype,
-                            void* disp_blk, void* vel_blk) {
+                            void* disp_blk, void* vel_blk, int64_t out_S0 = 0) {
   const bool blocks = disp_blk != nullptr;
+  if (out_S0 <= 0) out_S0 = size[0];          // D extent of the host output arrays (a streamed D-slab holds fewer planes)
   int rc = check_box_args(ctx, in_host, size, crop, plen, crop_idx, add_idx0, blocks ? disp_blk : disp_host,
                           blocks ? vel_blk : vel_host, sub_count, in_dtype, out_dtype);
   if (rc) return rc;
   if (sub_count == 0) return NBE_OK;
-  if ((rc = check_tables(ctx, size, crop, plen, crop_idx, add_idx0, sub_first, sub_count))) return rc;
+  if ((rc = check_tables(ctx, size, crop, plen, crop_idx, add_idx0, sub_first, sub_count, out_S0))) return rc;
   ENTER_DEVICE(ctx);
   cudaStream_t st = ctx->own_stream, cs = ctx->copy_stream, us = ctx->up_stream;
   const int64_t S0 = size[0], S1 = size[1], S2 = size[2];
@@ -1388,7 +1389,7 @@ static int process_box_host(nbe_ctx* ctx, const void* in_host, int in_dtype, con
       uint8_t* hdst = static_cast<uint8_t*>(f == 0 ? disp_host : vel_host);
       for (int c = 0; c < 3; ++c) {
         uint8_t* dch = dsrc + static_cast<size_t>(c) * ND * plane_out;            // device slab channel
-        uint8_t* hch = hdst + (static_cast<size_t>(c) * S0 + dlo) * plane_out;    // same planes in the host box
+        uint8_t* hch = hdst + (static_cast<size_t>(c) * out_S0 + dlo) * plane_out;    // same planes in the host box
         if (n_run == run_full) {
           const size_t off = static_cast<size_t>(a0[0]) * plane_out;
           CK(cudaMemcpyAsync(hch + off, dch + off, static_cast<size_t>(crop[0]) * plane_out, cudaMemcpyDeviceToHost, cs));
@@ -1469,7 +1470,7 @@ int nbe_process_box_blocks(nbe_ctx* ctx, const void* in_host, int in_dtype, cons
 int nbe_process_box_multi(nbe_ctx** ctxs, int ngpu, const void* in_host, int in_dtype, const int32_t size[3],
                           const int32_t crop[3], const int32_t plen[3], const int32_t* crop_idx, const int32_t* add_idx0,
                           int sub_first, int sub_count, float Dz, float vel_fac, void* disp_host, void* vel_host,
-                          int out_dtype) {
+                          int out_dtype, int32_t out_size0) {
   if (!ctxs || ngpu < 1) return NBE_ERR_ARG;
   for (int g = 0; g < ngpu; ++g) if (!ctxs[g]) return NBE_ERR_ARG;
   if (sub_count < 0) return fail(ctxs[0], NBE_ERR_ARG, "sub_count < 0");
@@ -1480,7 +1481,7 @@ int nbe_process_box_multi(nbe_ctx** ctxs, int ngpu, const void* in_host, int in_
     const int lo = g * base + std::min(g, rem), cnt = base + (g < rem ? 1 : 0);
     th.emplace_back([=, &rcs]() {
       rcs[g] = process_box_host(ctxs[g], in_host, in_dtype, size, crop, plen, crop_idx, add_idx0, sub_first + lo, cnt, Dz,
-                                vel_fac, disp_host, vel_host, out_dtype, nullptr, nullptr);
+                                vel_fac, disp_host, vel_host, out_dtype, nullptr, nullptr, out_size0);
     });
   }
   for (auto& t : th) t.join();

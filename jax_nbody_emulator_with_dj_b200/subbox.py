@@ -314,6 +314,83 @@ class SubboxProcessor:
             return dis, vel
         return dis
 
+    def process_box_streamed(self, plane_source, slab_sink, z, Om, devices=None, max_slabs=None):
+        """Boxes that fit neither host nor device memory (BASELINE config 5: 2048^3 = 103 GB in, 206 GB
+        out): the box is walked as ndiv[0] D-slabs of subboxes.  For slab k the caller's
+        ``plane_source(planes, out)`` fills ``out[:, j]`` (shape (C, len(planes), S1, S2), config.dtype)
+        with input plane ``planes[j]`` -- the slab's crop[0] planes plus the periodic 48-plane halo on
+        both sides -- into page-locked staging memory; every GPU pulls its (D, H) window straight from
+        that staging buffer (``nbe_process_box_multi``) and DMAs its finished blocks into a page-locked
+        output slab; ``slab_sink(k, d0, disp, vel)`` then receives (C, crop[0], S1, S2) views (valid only
+        during the call; ``vel`` is None for displacement-only models) of planes [d0, d0 + crop[0]).
+        Staging is double-buffered: while the GPUs run slab k, a second host thread fills slab k + 1 and
+        the sink drains slab k - 1.  Host memory: 2 x (crop[0]+96 input planes + crop[0] output planes per
+        field), whatever the box size.  The subboxes, their tables and their results are exactly
+        those of ``process_box`` (same kernels, same order): outputs are bit-identical.
+        Returns the number of slabs processed."""
+        from concurrent.futures import ThreadPoolExecutor
+        cfg = self.config
+        torch = _torch()
+        if self.params is None:
+            raise ValueError("No parameters loaded. Use load_params=True in create_emulator.")
+        in_np, out_np = np.dtype(cfg.dtype), np.dtype(cfg.output_dtype)
+        S0, S1, S2 = (int(v) for v in cfg.size)
+        n0, n1, n2 = (int(v) for v in cfg.ndiv)
+        c0 = int(cfg.crop_size[0])
+        p_lo, p_hi = (int(v) for v in cfg.padding[0])
+        P0 = c0 + p_lo + p_hi
+        Dz = np.float32(growth_factor(z, Om))
+        vf = np.float32(vel_norm(z, Om)) if self.compute_vel else np.float32(0)
+        dist = torch.distributed if torch.distributed.is_available() and torch.distributed.is_initialized() else None
+        engines = self._engines(devices, dist)
+        for eng in engines:
+            eng.set_precision(self.model.precision)
+            eng.set_params(self.params, self.premodulate, self.compute_vel, self.model.eps)
+            eng.modulate(None if self.premodulate else np.float32(Om), Dz)
+        if self._tables is None:
+            self._tables = cfg.flat_tables()
+        crop_idx, add0, plen = self._tables
+        per = sum(plen)
+        # slab-local tables: the staging buffer holds the slab's planes in gather order, so the D table
+        # is the identity and the D anchor is 0; H and W tables are those of the first slab's subboxes
+        nsl = n1 * n2
+        tab = crop_idx.reshape(-1, per)[:nsl].copy()
+        tab[:, :plen[0]] = np.arange(P0, dtype=np.int32)[None]
+        anc = add0.reshape(-1, 3)[:nsl].copy()
+        anc[:, 0] = 0
+        tab, anc = np.ascontiguousarray(tab.ravel()), np.ascontiguousarray(anc.ravel())
+        C_ = int(cfg.in_chan)
+        nf = 2 if self.compute_vel else 1
+        inb = [_pinned_zeros((C_, P0, S1, S2), in_np) for _ in range(2)]
+        outb = [[_pinned_zeros((C_, c0, S1, S2), out_np) for _ in range(nf)] for _ in range(2)]
+        n_slabs = n0 if max_slabs is None else min(n0, int(max_slabs))
+
+        def fill(k):
+            planes = (k * c0 - p_lo + np.arange(P0)) % S0
+            plane_source(planes, inb[k % 2][1])
+
+        def run(k):
+            o = outb[k % 2]
+            Engine.process_box_multi(engines, inb[k % 2][1], dtype_code(in_np), (P0, S1, S2), cfg.crop_size, plen, tab, anc,
+                                     0, nsl, Dz, vf, o[0][1], o[1][1] if self.compute_vel else None, dtype_code(out_np),
+                                     out_size0=c0)
+
+        def sink(k):
+            o = outb[k % 2]
+            slab_sink(k, k * c0, o[0][1], o[1][1] if self.compute_vel else None)
+
+        with ThreadPoolExecutor(max_workers=1) as ex:
+            fill(0)
+            for k in range(n_slabs):
+                fut = ex.submit(run, k)
+                if k + 1 < n_slabs:
+                    fill(k + 1)
+                if k > 0:
+                    sink(k - 1)
+                fut.result()
+            sink(n_slabs - 1)
+        return n_slabs
+
     def _process_gather_nccl(self, dist, cfg, eng, box, in_np, out_np, plen, crop_idx, add0, lo, hi, n, rank, world,
                              Dz, vf, gather, copy):
         """One process per GPU: this rank's subboxes stay on its GPU as (count, 3, c0, c1, c2) records,
