@@ -1348,8 +1348,17 @@ static int process_box_host(nbe_ctx* ctx, const void* in_host, int in_dtype, con
             uint8_t* dst = static_cast<uint8_t*>(ctx->d_box) + ((static_cast<size_t>(c) * nD + ud[i]) * nH + run.first) * row_in;
             const uint8_t* src = static_cast<const uint8_t*>(in_host) +
                                  ((static_cast<size_t>(c) * S0 + srcD[ud[i]]) * S1 + srcH[run.first]) * row_in;
+            // own bounds check of every rectangle (compute-sanitizer is not available on this pool): last byte
+            // written / read must lie inside the device window / the caller's box
+            const size_t n_rows = j - i + 1, w_bytes = static_cast<size_t>(run.second) * row_in;
+            const size_t dst_end = static_cast<size_t>(dst - static_cast<uint8_t*>(ctx->d_box)) + (n_rows - 1) * nH * row_in + w_bytes;
+            const size_t src_end = static_cast<size_t>(src - static_cast<const uint8_t*>(in_host)) + (n_rows - 1) * S1 * row_in + w_bytes;
+            if (dst_end > in_bytes || src_end > static_cast<size_t>(3) * S0 * S1 * row_in) {
+              cudaStreamSynchronize(us); destroy_events();
+              return fail(ctx, NBE_ERR_STATE, "process_box upload: rectangle out of bounds (internal error)");
+            }
             cudaError_t e = cudaMemcpy2DAsync(dst, static_cast<size_t>(nH) * row_in, src, static_cast<size_t>(S1) * row_in,
-                                              static_cast<size_t>(run.second) * row_in, j - i + 1, cudaMemcpyHostToDevice, us);
+                                              w_bytes, n_rows, cudaMemcpyHostToDevice, us);
             if (e != cudaSuccess) {
               cudaStreamSynchronize(us); destroy_events();
               return fail(ctx, NBE_ERR_CUDA, "process_box upload: %s", cudaGetErrorString(e));

@@ -12,7 +12,10 @@ hi+lo pair, id = plain fp32):
   deep   prod, but the small deep blocks (conv_l2 .. conv_r2) in fp32
   deep2  prod, but the deep blocks with hi+lo tangent operands (r2) and primal fp32
   tact   prod with hi+lo tangent ACTIVATIONS (xt, dx = r2; dW, W in the tangent = r1)
-Results are appended as JSON lines to profiles/r2_velocity_sweep.jsonl.
+Results are appended as JSON lines to profiles/r2_velocity_sweep.jsonl; the fp64 outputs go to
+tests/golden/sweep/<geom>_<seed>.npz (float32; with the emulated product error when it was computed) --
+the GPU seed-sweep test (tests/test_gpu_parity.py::test_velocity_seed_sweep) checks the kernels against
+them.  A 5th argument "truth" computes only the fp64 outputs (seeds whose variants are already logged).
 """
 import json, os, sys, time
 import numpy as np, torch
@@ -22,6 +25,8 @@ from oracle import cosmology as oc
 
 geom, seed0, nseeds = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 torch.set_num_threads(int(sys.argv[4]) if len(sys.argv) > 4 else 6)
+truth_only = len(sys.argv) > 5 and sys.argv[5] == "truth"
+os.makedirs('tests/golden/sweep', exist_ok=True)
 P = init_params(42)
 shape, z, Om = {'nc': ((104, 112, 120), 1.0, 0.25), 'n128': ((128, 128, 128), 0.5, 0.3),
                 'n104': ((104, 104, 104), 0.5, 0.3)}[geom]
@@ -51,12 +56,15 @@ for seed in range(seed0, seed0 + nseeds):
     with torch.no_grad():
         d64, v64 = [t.numpy() for t in Net(True, True, torch.float64).forward(P, x, float(np.float32(Om)), Dz, vf)]
         row = dict(geom=geom, shape=shape, seed=seed, z=z, Om=Om)
-        for name, (o, byb) in variants.items():
+        for name, (o, byb) in ({} if truth_only else variants).items():
             net = Net(True, True, torch.float32, ops=o)
             net.ops_by_block = byb
             d, v = [t.numpy() for t in net.forward(P, x, float(np.float32(Om)), Dz, vf)]
             row[name] = [rel_l2(d, d64), rel_l2(v, v64)]
     row['sec'] = round(time.time() - t0)
-    with open(out, 'a') as f:
-        f.write(json.dumps(row) + '\n')
+    np.savez_compressed(f'tests/golden/sweep/{geom}_{seed}.npz', disp=d64.astype(np.float32), vel=v64.astype(np.float32),
+                        seed=seed, shape=shape, z=z, Om=Om)
+    if not truth_only:
+        with open(out, 'a') as f:
+            f.write(json.dumps(row) + '\n')
     print(json.dumps(row), flush=True)
