@@ -179,12 +179,14 @@ class Engine:
             self.precision = precision
             self._mod_key = None
 
-    def set_params(self, params, premod, vel, eps=1e-8):
+    def set_params(self, params, premod, vel, eps=1e-8, fingerprint=None):
         """Upload the tree unless the SAME tree with the same leaves was uploaded last.  The cache key
         holds the identity, address and shape of every leaf plus a strided content sample, so replacing
         a leaf (``params['params'][b][l]['weight'] = w2``) or overwriting one in place is seen; call
         ``invalidate()`` after any other kind of in-place edit."""
-        key = (id(params), bool(premod), bool(vel), float(eps), params_fingerprint(params))
+        if fingerprint is None:
+            fingerprint = params_fingerprint(params)
+        key = (id(params), bool(premod), bool(vel), float(eps), fingerprint)
         if key == self._params_key and self._params_ref is params:
             return
         arr, keep = flatten_params(params, premod, vel)

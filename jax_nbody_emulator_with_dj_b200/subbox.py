@@ -16,7 +16,7 @@ from typing import Any
 import numpy as np
 
 from . import _lib
-from ._engine import Engine, dtype_code, _torch
+from ._engine import Engine, dtype_code, params_fingerprint, _torch
 from .cosmology import growth_factor, vel_norm
 
 
@@ -142,6 +142,7 @@ class SubboxProcessor:
         self._pool = _OutputPool()
         self._pinned_in = None     # (key, array, registered-by-us) of the host input currently page-locked
         self.last_gather = None    # {"bytes", "ms", "GBps"} of the most recent NCCL output gather
+        self.time_gather = False   # True: align the ranks with a barrier first, so "ms" is the collective alone
 
     def close(self):
         """Release the page-lock on the cached input buffer (also called on garbage collection: a
@@ -256,9 +257,10 @@ class SubboxProcessor:
         lo, hi = shard_range(n, rank, world)
 
         engines = self._engines(devices, dist)
+        fp = params_fingerprint(self.params)           # once per call, shared by all GPUs' engines
         for eng in engines:
             eng.set_precision(self.model.precision)
-            eng.set_params(self.params, self.premodulate, self.compute_vel, self.model.eps)
+            eng.set_params(self.params, self.premodulate, self.compute_vel, self.model.eps, fingerprint=fp)
             eng.modulate(None if self.premodulate else np.float32(Om), Dz)
         eng = engines[0]
         if tables is None:
@@ -412,6 +414,9 @@ class SubboxProcessor:
                                send[0], send[1] if self.compute_vel else None, dtype_code(out_np))
         recv = torch.empty((world, nf, n_max) + rec, dtype=tdt, device=dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if self.time_gather:       # ranks finish their subboxes at different times: without this the interval
+            dist.barrier()         # measures the wait for the slowest rank, not the transfer
+            torch.cuda.synchronize(dev)
         e0.record()
         dist.all_gather_into_tensor(recv.view(-1), send.view(-1))
         e1.record()
@@ -440,6 +445,7 @@ class SubboxProcessor:
         ms = e0.elapsed_time(e1)
         nbytes = recv.numel() * recv.element_size()
         self.last_gather = {"bytes": int(nbytes), "ms": float(ms), "GBps": nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                            "ranks_aligned": bool(self.time_gather),
                             "collective": "ncclAllGather of (subbox, 3, c0, c1, c2) records, device to device"}
         if self.compute_vel:
             return outs[0], outs[1]

@@ -11,13 +11,17 @@ local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
-size, ndiv = (256, 256, 256), (2, 2, 2)
+S = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+nd = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+size, ndiv = (S, S, S), (nd, nd, nd)
 box = np.random.default_rng(7).standard_normal((3,) + size, dtype=np.float32)
 proc = nb.SubboxProcessor(nb.StyleNBodyEmulatorVelCore(), nb.init_params(42), nb.SubboxConfig(size=size, ndiv=ndiv))
 d, v = proc.process_box(box, 0.5, 0.3, show_progress=False)                       # sharded + NCCL all-gather (default)
 g = dict(proc.last_gather)
+proc.time_gather = True
 d, v = proc.process_box(box, 0.5, 0.3, show_progress=False)                       # warm: communicator and buffers exist
 g = dict(proc.last_gather)
+proc.time_gather = False
 d1, v1 = proc.process_box(box, 0.5, 0.3, show_progress=False, shard=(0, 1), gather="none")   # this rank alone
 ok = torch.tensor([int(np.array_equal(d, d1) and np.array_equal(v, v1))], device="cuda")
 dist.all_reduce(ok, op=dist.ReduceOp.MIN)
