@@ -30,8 +30,10 @@ struct EmitRule {
   int16_t mod;
   int8_t cta_base;
   int8_t kd_mask;     // bit kd set: the rule applies to taps of that kd-plane (0: all)
+  // explicit form (o_max > 0): output channels [o_min, o_max) go to CTA `cta_base`, rows row_base + (o - o_min)
+  int16_t o_min, o_max;
 };
-constexpr int kMaxRules = 10;
+constexpr int kMaxRules = 16;
 
 struct LayerMeta {
   const float* W;        // (cout, cin, k3) raw weight, or premodulated weight
@@ -138,8 +140,10 @@ modulate_kernel(const LayerMeta* __restrict__ metas, int n_layers, const float* 
       const int col = M.kc16 ? (R.kcol + i) : (i & 63);
       const int kd = M.k3 == 27 ? tap / 9 : 0;
       if (R.kd_mask && !((R.kd_mask >> kd) & 1)) continue;
-      const int row = R.mod ? ((o / R.mod + R.cta_base) * M.pair_rows + R.row_base + o % R.mod)
-                            : (R.row_base + (kd == 1 ? R.alt_kd1 : 0) + o);
+      if (R.o_max > 0 && (o < R.o_min || o >= R.o_max)) continue;
+      const int row = R.o_max > 0 ? (R.cta_base * M.pair_rows + R.row_base + (o - R.o_min))
+                      : R.mod ? ((o / R.mod + R.cta_base) * M.pair_rows + R.row_base + o % R.mod)
+                              : (R.row_base + (kd == 1 ? R.alt_kd1 : 0) + o);
       M.dst[sample_off + (tile * M.nrs + row) * rowlen + col] = v;
     }
   }

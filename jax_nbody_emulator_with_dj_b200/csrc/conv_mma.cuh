@@ -31,7 +31,7 @@ constexpr float kWeightScale = 256.0f;          // packed weights carry this fac
 constexpr float kInvWeightScale = 1.0f / 256.0f;
 
 struct MmaOp {
-  uint16_t a_off;   // byte offset >> 4 of the A operand block inside the activation stage
+  uint16_t a_off;   // index (0 / 1) of the group's activation block this op multiplies
   uint16_t b_off;   // byte offset >> 4 of the first B row inside the weight stage
   uint16_t d_col;   // first accumulator column
   uint8_t n8;       // N / 8
@@ -53,7 +53,8 @@ struct GroupDesc {
   int8_t post_sig;    // after this group commit           1: y0_full   2: y1_full
   int8_t lo_stage;    // weight stages of this group use the short box of bmap64_lo (lo products)
   int32_t brow0;      // B row of tap 0
-  int32_t brow_step;  // B rows between consecutive taps
+  int16_t brow_step;  // B rows between consecutive taps
+  int16_t tap_rows;   // rows between consecutive taps INSIDE a multi-tap weight stage (this CTA's rows per tap)
   MmaOp ops[3];
 };
 
@@ -69,8 +70,10 @@ struct alignas(128) ConvLaunch {
   CUtensorMap amap[kMaxAMaps];
   CUtensorMap bmap64;
   CUtensorMap bmap16;
-  CUtensorMap bmap64_lo;    // same tensor as bmap64 with a box of lo_rows rows (lo-product stages use fewer rows)
+  CUtensorMap bmap64_lo;    // same tensor as bmap64 with a box of lo_rows rows (lo-product stages use fewer rows);
+                            // lo_taps == 3: a 3-D map {64, rows, tiles} whose box carries three consecutive taps
   int32_t lo_rows;          // rows per CTA of a lo stage (0: lo stages use bmap64)
+  int32_t lo_taps;          // taps per lo-stage box: 1 or 3
   int32_t n_par;            // 1, or 8 for the x2 up-sampling conv (one parity per item)
   int32_t par_brow_step;    // B rows between parities
   int32_t out_w, out_h, out_d;         // extent of the tile space
@@ -137,6 +140,9 @@ struct ConvCfg {
   static constexpr int kBRows = PAIR ? NRS / 2 : NRS;       // rows this CTA stages per tap
   static constexpr int kBStage = kBRows * 128;
   static constexpr int kNA = (TM == 1) ? 3 : 2;
+  // The activation ring is a ring of BLOCKS: a group takes as many consecutive slots as it has operand
+  // blocks (1 or 2), so the one-block groups of a lo phase leave room to prefetch further ahead.
+  static constexpr int kNAB = 2 * kNA;
   static constexpr int kCtrl = 2048;                       // barriers, TMEM slot, bias
   static constexpr int kBudget = kSmemLimit - 1024 /*align*/ - kCtrl - kNA * kAStage;
   static constexpr int kNBraw = kBudget / kBStage;
@@ -166,7 +172,17 @@ constexpr bool kBaseOffsetMode = NBE_BASE_OFFSET != 0;
 // under the epilogue's math and stores: the single-buffered TMEM no longer idles the tensor pipe.
 // Same MMAs per accumulator in the same order and the same (y0 + y1) + y2 sum: bit-identical to the
 // plain acc3 path.
-template <int NRS, int DC, int TM, bool FINAL, bool PAIR = false, bool EARLY = false>
+//
+// EARLY == 2 ("F192", 64-output pair instance): columns [y1 | dy | ylo | y0].  The three products that
+// share the activation operand xh are ONE instruction per k-step, N = 192: weight rows [dW | Wl | Wh]
+// land on (dy, ylo, y0) for kd 0 / 2 and rows [Wh | dW | Wl] on (y1, dy, ylo) for kd 1; dx * Wh -> dy
+// (N = 64) is the second; the lo phase is the single product xl * Wh (N = 64) accumulated into y1 BEFORE
+// kd 1's hi products.  Per k-step that is 3 MMAs and 3 activation-operand reads instead of 4.33, and
+// xh is fetched by TMA once per kd-plane, not twice.  kd 2 re-uses the y0 columns: the epilogue drains
+// y0 (then y1) while kd 1 (kd 2) runs, the issuers wait for y0_empty before kd 2, and the next item's
+// lo phase needs only y1 (drained during kd 2), so the end-of-item drain of (dy, ylo, y0') hides under it.
+// Sum order ((y0 + y1) + y0') + ylo.
+template <int NRS, int DC, int TM, bool FINAL, bool PAIR = false, int EARLY = 0>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupTable gt,
                 const __grid_constant__ FinalArgs fa) {
@@ -179,16 +195,18 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
   uint8_t* b_smem = a_smem + Cfg::kNA * Cfg::kAStage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + Cfg::kNB * Cfg::kBStage);
   uint64_t* a_full = bars;
-  uint64_t* a_empty = a_full + Cfg::kNA;
-  uint64_t* b_full = a_empty + Cfg::kNA;
+  uint64_t* a_empty = a_full + Cfg::kNAB;
+  uint64_t* b_full = a_empty + Cfg::kNAB;
   uint64_t* b_empty = b_full + Cfg::kNB;
   uint64_t* acc_full = b_empty + Cfg::kNB;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* y0_full = acc_empty + 2;       // EARLY only
   uint64_t* y1_full = y0_full + 1;
   uint64_t* y0_empty = y1_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y0_empty + 1);
-  static_assert(!EARLY || (Cfg::kNBuf == 1 && !FINAL && TM * DC == 512), "EARLY: single-stage acc3 instances only");
+  uint64_t* y1_empty = y0_empty + 1;       // EARLY == 2 only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y1_empty + 1);
+  static_assert(EARLY == 0 || (Cfg::kNBuf == 1 && !FINAL && TM * DC == 512), "EARLY: single-stage acc3 instances only");
+  static_assert(EARLY != 2 || (PAIR && TM == 2 && DC == 256), "F192: 64-output pair instance only");
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);   // up to 128 floats
 
   const int warp = threadIdx.x >> 5;
@@ -209,10 +227,11 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
   if (threadIdx.x == 0) {
     // kIssuers MMA-issuing warps (one per M-tile when TM == 2): each commits to the empty / full
     // barriers, so those expect kIssuers arrivals
-    for (int i = 0; i < Cfg::kNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], kIssuers); }
+    for (int i = 0; i < Cfg::kNAB; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], kIssuers); }
     for (int i = 0; i < Cfg::kNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], kIssuers); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], kIssuers); mbar_init(&acc_empty[i], PAIR ? 512 : 256); }
     mbar_init(y0_full, kIssuers); mbar_init(y1_full, kIssuers); mbar_init(y0_empty, PAIR ? 512 : 256);
+    mbar_init(y1_empty, PAIR ? 512 : 256);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -297,17 +316,17 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
         for (int g = 0; g < n_groups; ++g) {
           const GroupDesc& G = gt.g[g];
           const uint32_t blk = static_cast<uint32_t>(Cfg::kHRows) * G.pitch * (G.kc16 ? 32u : 128u);
-          mbar_wait(&a_empty[s], ph ^ 1);
-          if (!PAIR || rank == 0) mbar_expect_tx(&a_full[s], blk * G.n_a * (PAIR ? 2 : 1));
           for (int q = 0; q < G.n_a; ++q) {
+            mbar_wait(&a_empty[s], ph ^ 1);
+            if (!PAIR || rank == 0) mbar_expect_tx(&a_full[s], blk * (PAIR ? 2 : 1));
             if constexpr (PAIR)
-              tma_load_4d_2sm(a_smem + s * Cfg::kAStage + q * Cfg::kABlk, &L->amap[G.a_map[q]], &a_full[s],
+              tma_load_4d_2sm(a_smem + s * Cfg::kABlk, &L->amap[G.a_map[q]], &a_full[s],
                               G.c0, w0 + G.dw, h0 + G.dh, d0 + G.dd);
             else
-              tma_load_4d(a_smem + s * Cfg::kAStage + q * Cfg::kABlk, &L->amap[G.a_map[q]], &a_full[s],
+              tma_load_4d(a_smem + s * Cfg::kABlk, &L->amap[G.a_map[q]], &a_full[s],
                           G.c0, w0 + G.dw, h0 + G.dh, d0 + G.dd);
+            if (++s == Cfg::kNAB) { s = 0; ph ^= 1; }
           }
-          if (++s == Cfg::kNA) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -316,7 +335,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
       const int par_brow_step = L->par_brow_step;
-      const int lo_rows = L->lo_rows;
+      const int lo_rows = L->lo_rows, lo_taps = L->lo_taps;
       for (long long it0 = item_first; it0 < n_items; it0 += gridDim.x) {
         int par, w0, h0, d0;
         decode(it0, par, w0, h0, d0);
@@ -332,6 +351,13 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
             uint8_t* dst = b_smem + s * Cfg::kBStage;
             if (G.kc16) {
               // 16-channel tiles: one 3-D box {16 ch, this CTA's rows, 3 consecutive taps} per stage
+              if (!PAIR || rank == 0) mbar_expect_tx(&b_full[s], bytes * 3 * (PAIR ? 2 : 1));
+              const int tile = (G.brow0 + par * par_brow_step) / NRS + j;
+              const int r0 = PAIR ? static_cast<int>(rank) * Cfg::kBRows : 0;
+              if constexpr (PAIR) tma_load_3d_2sm(dst, bm, &b_full[s], 0, r0, tile);
+              else tma_load_3d(dst, bm, &b_full[s], 0, r0, tile);
+            } else if (lo_box && lo_taps == 3) {
+              // three taps of lo rows per stage (the box always carries three tiles; a one-tap group uses the first)
               if (!PAIR || rank == 0) mbar_expect_tx(&b_full[s], bytes * 3 * (PAIR ? 2 : 1));
               const int tile = (G.brow0 + par * par_brow_step) / NRS + j;
               const int r0 = PAIR ? static_cast<int>(rank) * Cfg::kBRows : 0;
@@ -364,7 +390,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0, buf = 0, pacc = 0;
     for (long long item = item_first; item < n_items && (!PAIR || rank == 0); item += gridDim.x) {
-      if constexpr (!EARLY) {
+      if constexpr (EARLY == 0) {
         mbar_wait(&acc_empty[buf], pacc ^ 1);
         tc_fence_after();
       }
@@ -372,10 +398,13 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
       for (int g = 0; g < n_groups; ++g) {
         const GroupDesc& G = gt.g[g];
         const int ntaps = G.ntaps, n_ops = G.n_ops;
-        if constexpr (EARLY) {
+        if constexpr (EARLY != 0) {
+          // pre_wait 1: y0_empty, 2: acc_empty, 3: y1_empty.  All are signalled by the PREVIOUS item's
+          // epilogue, except y0_empty in the F192 layout, which kd 2 needs from the CURRENT item
           const int pw = G.pre_wait;
           if (pw != 0) {
-            mbar_wait(pw == 1 ? y0_empty : &acc_empty[0], pacc ^ 1);
+            uint64_t* bar = pw == 1 ? y0_empty : (pw == 2 ? &acc_empty[0] : y1_empty);
+            mbar_wait(bar, (EARLY == 2 && pw == 1) ? pacc : (pacc ^ 1));
             tc_fence_after();
           }
         }
@@ -388,19 +417,31 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
         // upper descriptor word: SBO | version | layout
         const uint32_t desc_hi = sbo16 | (1u << 14) | ((k16 ? 6u : 2u) << 29);
         const uint32_t bdesc_hi = bsbo16 | (1u << 14) | ((k16 ? 6u : 2u) << 29);
+        // the group's operand blocks sit in n_a consecutive ring slots (with wrap-around).  Slot
+        // arithmetic is kept branch-free: everything the MMA descriptors are built from must stay in
+        // uniform registers (an R2UR per operand word in front of every UTCHMMA -- which is what a
+        // conditional wait loop over the slots, or a __shfl_sync broadcast, produced -- costs a third
+        // of the whole net).
+        uint32_t a_blk1;
+        {
+          const uint32_t s1 = (sa + 1 == Cfg::kNAB) ? 0u : sa + 1;
+          mbar_wait(&a_full[sa], pa);
+          if (G.n_a == 2) mbar_wait(&a_full[s1], (sa + 1 == Cfg::kNAB) ? (pa ^ 1u) : pa);
+          a_blk1 = ((smem_u32(a_smem + s1 * Cfg::kABlk) & 0x3FFFFu) >> 4) | (1u << 16);
+        }
+        tc_fence_after();
+        const uint32_t a_blk0 = ((smem_u32(a_smem + sa * Cfg::kABlk) & 0x3FFFFu) >> 4) | (1u << 16);
         uint32_t op_a[3], op_b[3], op_d[3], op_i[3];
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
-          op_a[o] = G.ops[o].a_off;
+          op_a[o] = (G.ops[o].a_off & 1) ? a_blk1 : a_blk0;
           op_b[o] = G.ops[o].b_off;
           op_d[o] = G.ops[o].d_col;
           op_i[o] = idesc_base | (static_cast<uint32_t>(G.ops[o].n8) << 17);
         }
-        mbar_wait(&a_full[sa], pa);
-        tc_fence_after();
-        const uint32_t a_lo = ((smem_u32(a_smem + sa * Cfg::kAStage) & 0x3FFFFu) >> 4) | (1u << 16);
         const int tps = G.tps;
-        const uint32_t tap16 = static_cast<uint32_t>(Cfg::kBRows) * row16;   // one tap's tile in 16-byte units
+        // one tap's rows inside a multi-tap stage, in 16-byte units (lo stages carry lo_rows per tap)
+        const uint32_t tap16 = static_cast<uint32_t>(G.tap_rows) * row16;
         if (k16 && tps == 3) {
           // 16-channel rows: one MMA per tap, so the per-tap wait / elect / commit round trip (about 400
           // cycles of dependent uniform instructions) was the limiter of the first layer; issue the three
@@ -418,11 +459,11 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
                   const uint32_t kw = ntaps == 9 ? jj / 3u : 0u;
                   const uint32_t kh = ntaps == 9 ? jj % 3u : jj;
                   const uint32_t a_row = (static_cast<uint32_t>(my_tile * 16) + kh) * sbo16 + kw * row16;
-                  const uint32_t a_hi = desc_hi | (kBaseOffsetMode ? (((a_lo + a_row) >> 3) & 7u) << 17 : 0u);
+                  const uint32_t a_hi = desc_hi | (kBaseOffsetMode ? (((a_blk0 + a_row) >> 3) & 7u) << 17 : 0u);
 #pragma unroll
                   for (int o = 0; o < 3; ++o)
                     if (o < n_ops)
-                      mma(d_tile + op_d[o], (static_cast<uint64_t>(a_hi) << 32) | (a_lo + op_a[o] + a_row),
+                      mma(d_tile + op_d[o], (static_cast<uint64_t>(a_hi) << 32) | (op_a[o] + a_row),
                           (static_cast<uint64_t>(bdesc_hi) << 32) | (b_base + jt * tap16 + op_b[o]), op_i[o], 1u);
                 }
               }
@@ -451,12 +492,12 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
               // B200: the MMA unit swizzles on absolute smem address bits (like TMA), so the plain
               // shifted start with base_offset = 0 is correct; setting base_offset = (addr>>7)&7 is
               // WRONG (NBE_BASE_OFFSET=1 reproduces that experiment).
-              const uint32_t a_hi = desc_hi | (kBaseOffsetMode ? (((a_lo + a_row) >> 3) & 7u) << 17 : 0u);
+              const uint32_t a_hi = desc_hi | (kBaseOffsetMode ? (((a_blk0 + a_row) >> 3) & 7u) << 17 : 0u);
               if (k16) {
 #pragma unroll
                 for (int o = 0; o < 3; ++o)
                   if (o < n_ops)
-                    mma(d_tile + op_d[o], (static_cast<uint64_t>(a_hi) << 32) | (a_lo + op_a[o] + a_row),
+                    mma(d_tile + op_d[o], (static_cast<uint64_t>(a_hi) << 32) | (op_a[o] + a_row),
                         (static_cast<uint64_t>(bdesc_hi) << 32) | (b_lo + op_b[o]), op_i[o], 1u);
               } else {
 #pragma unroll
@@ -465,7 +506,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
                   for (int o = 0; o < 3; ++o)
                     if (o < n_ops)
                       mma(d_tile + op_d[o],
-                          (static_cast<uint64_t>(a_hi) << 32) | (a_lo + op_a[o] + a_row + 2u * k),
+                          (static_cast<uint64_t>(a_hi) << 32) | (op_a[o] + a_row + 2u * k),
                           (static_cast<uint64_t>(bdesc_hi) << 32) | (b_lo + op_b[o] + 2u * k), op_i[o], 1u);
                 }
               }
@@ -478,14 +519,19 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
             if (++sb == Cfg::kNB) { sb = 0; pb ^= 1; }
           }
         }
-        const int ps = EARLY ? G.post_sig : 0;
+        const int ps = EARLY != 0 ? G.post_sig : 0;
         if (elect_one()) {
           commit(&a_empty[sa]);
+          if (G.n_a == 2) commit(&a_empty[sa + 1 == Cfg::kNAB ? 0u : sa + 1]);
           if (ps == 1) commit(y0_full);
           else if (ps == 2) commit(y1_full);
         }
         __syncwarp();
-        if (++sa == Cfg::kNA) { sa = 0; pa ^= 1; }
+        {
+          const uint32_t adv = sa + static_cast<uint32_t>(G.n_a);
+          pa ^= (adv >= Cfg::kNAB) ? 1u : 0u;
+          sa = (adv >= Cfg::kNAB) ? adv - Cfg::kNAB : adv;
+        }
       }
       if (elect_one()) commit(&acc_full[buf]);
       __syncwarp();
@@ -510,10 +556,16 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     __half* const out_l_ptr = L->out_l_ptr;
     __half* const out_d_ptr = L->out_d_ptr;
     uint32_t buf = 0, pacc = 0;
-    if constexpr (EARLY) {
-      // [y0 | dy | y1 | y2] x COUT columns per tile; this thread owns row r of tile t and the two
-      // 32-channel chunks ch(0), ch(1) (TM == 1: the warp sets take alternate chunks of the 128)
+    if constexpr (EARLY != 0) {
+      // EARLY == 1: [y0 | dy | y1 | y2],  EARLY == 2: [y1 | dy | ylo | y0]  (x COUT columns per tile); this
+      // thread owns row r of tile t and the two 32-channel chunks ch(0), ch(1) (TM == 1: the warp sets
+      // take alternate chunks of the 128)
       constexpr int COUT = DC / 4;
+      constexpr int cY0 = EARLY == 2 ? 3 * COUT : 0;          // first primal accumulator to complete
+      constexpr int cY1 = EARLY == 2 ? 0 : 2 * COUT;          // second
+      constexpr int cYZ = 3 * COUT;                           // last: y2, or y0 re-used by kd 2
+      constexpr int cDY = COUT;
+      constexpr int cLO = 2 * COUT;                           // F192 only: xh * Wl
       const int t = TM == 2 ? eg : 0;
       auto ch = [&](int i) { return TM == 1 ? eg * 32 + 64 * i : 32 * i; };
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * DC;
@@ -534,15 +586,15 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
         mbar_wait(y0_full, pacc);
         tc_fence_after();
         if (!dead) {
-          tmem_ld32(taddr + ch(0), ps);
-          tmem_ld32(taddr + ch(1), ps + 32);
+          tmem_ld32(taddr + cY0 + ch(0), ps);
+          tmem_ld32(taddr + cY0 + ch(1), ps + 32);
           tmem_ld_wait();
-          tmem_st32_zero(taddr + ch(0));
-          tmem_st32_zero(taddr + ch(1));
+          tmem_st32_zero(taddr + cY0 + ch(0));
+          tmem_st32_zero(taddr + cY0 + ch(1));
           tmem_st_wait();
         }
         tc_fence_before();
-        arrive(y0_empty);                         // the next item's lo products may start
+        arrive(y0_empty);                         // EARLY 1: the next item's lo products may start; 2: kd 2 may start
         // ---- y1
         mbar_wait(y1_full, pacc);
         tc_fence_after();
@@ -550,15 +602,20 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             uint32_t y1[32];
-            tmem_ld32(taddr + 2 * COUT + ch(i), y1);
+            tmem_ld32(taddr + cY1 + ch(i), y1);
             tmem_ld_wait();
-            tmem_st32_zero(taddr + 2 * COUT + ch(i));
+            tmem_st32_zero(taddr + cY1 + ch(i));
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               ps[32 * i + j] = __float_as_uint(__uint_as_float(ps[32 * i + j]) + __uint_as_float(y1[j]));
           }
         }
-        // ---- y2, dy: end of the item
+        if constexpr (EARLY == 2) {
+          tmem_st_wait();
+          tc_fence_before();
+          arrive(y1_empty);                       // the next item's lo phase (xl * Wh -> y1) may start
+        }
+        // ---- last primal accumulator, dy (and ylo): end of the item
         mbar_wait(&acc_full[0], pacc);
         tc_fence_after();
         if (!dead) {
@@ -569,17 +626,25 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
               const int c = ch(i) + 16 * hf;
-              uint32_t y2[16], dy[16];
-              tmem_ld16(taddr + 3 * COUT + c, y2);
-              tmem_ld16(taddr + COUT + c, dy);
+              uint32_t y2[16], dy[16], yl[16];
+              tmem_ld16(taddr + cYZ + c, y2);
+              tmem_ld16(taddr + cDY + c, dy);
+              if constexpr (EARLY == 2) tmem_ld16(taddr + cLO + c, yl);
               tmem_ld_wait();
-              tmem_st16_zero(taddr + 3 * COUT + c);
-              tmem_st16_zero(taddr + COUT + c);
+              tmem_st16_zero(taddr + cYZ + c);
+              tmem_st16_zero(taddr + cDY + c);
+              if constexpr (EARLY == 2) tmem_st16_zero(taddr + cLO + c);
               uint32_t ph[8], pl[8], pd[8];
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
-                float y0v = (__uint_as_float(ps[32 * i + 16 * hf + j]) + __uint_as_float(y2[j])) * kInvWeightScale + bias_s[c + j];
-                float y1v = (__uint_as_float(ps[32 * i + 16 * hf + j + 1]) + __uint_as_float(y2[j + 1])) * kInvWeightScale + bias_s[c + j + 1];
+                float s0 = __uint_as_float(ps[32 * i + 16 * hf + j]) + __uint_as_float(y2[j]);
+                float s1 = __uint_as_float(ps[32 * i + 16 * hf + j + 1]) + __uint_as_float(y2[j + 1]);
+                if constexpr (EARLY == 2) {
+                  s0 += __uint_as_float(yl[j]);
+                  s1 += __uint_as_float(yl[j + 1]);
+                }
+                float y0v = s0 * kInvWeightScale + bias_s[c + j];
+                float y1v = s1 * kInvWeightScale + bias_s[c + j + 1];
                 float d0v = __uint_as_float(dy[j]) * kInvWeightScale;
                 float d1v = __uint_as_float(dy[j + 1]) * kInvWeightScale;
                 if (act) {

@@ -31,8 +31,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 enum ConvType { T_CONV3 = 0, T_SKIP1 = 1, T_DOWN = 2, T_UP = 3 };
-enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_PAIR_256_512_1, I_PAIR_128_128_2, I_PAIR_256_256_1, I_PAIR_128_256_1, I_EARLY_128_256_2, I_EARLY_256_512_1, I_COUNT };
-struct InstInfo { int nrs, dc, tm; bool fin; bool pair = false; bool acc3 = false; bool early = false; };
+enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_PAIR_256_512_1, I_PAIR_128_128_2, I_PAIR_256_256_1, I_PAIR_128_256_1, I_EARLY_128_256_2, I_EARLY_256_512_1, I_F192_2, I_COUNT };
+struct InstInfo { int nrs, dc, tm; bool fin; bool pair = false; bool acc3 = false; bool early = false; bool f192 = false; };
 const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32, 16, 2, true},
                                  {128, 64, 2, false},  {64, 64, 2, false},   {256, 128, 1, false},
                                  {128, 256, 2, false, false, true}, {256, 512, 1, false, false, true},
@@ -42,7 +42,9 @@ const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32
                                  // one tile per CTA, two accumulator stages: the acc3 epilogue overlaps the next item
                                  {192, 256, 1, false, true, true},
                                  // early-drain acc3 pair instances (fine-grained accumulator hand-over, conv_mma.cuh)
-                                 {192, 256, 2, false, true, true, true}, {384, 512, 1, false, true, true, true}};
+                                 {192, 256, 2, false, true, true, true}, {384, 512, 1, false, true, true, true},
+                                 // F192: N = 192 fused [Wh|dW|Wl] main product, 2 x 128 weight rows per stage (conv_mma.cuh, EARLY == 2)
+                                 {256, 256, 2, false, true, true, true, true}};
 
 // activation tensors of the net
 enum ActId {
@@ -112,6 +114,7 @@ struct nbe_ctx {
   bool dbuf = false;        // 64-output acc3 pair launches: one tile per CTA + double-buffered TMEM (NBE_DBUF=0: two tiles)
   bool early = true;        // acc3 pair launches hand the per-kd accumulators over as they complete (NBE_EARLY=0: whole item)
   bool lo_box = true;       // lo-product weight stages are loaded with a box of only the rows they use (NBE_LOBOX=0)
+  bool f192 = true;         // 64-output acc3 pair launches use the N = 192 fused instance (NBE_F192=0: EARLY / plain)
   int band_h = 2;           // tile rows per h-band of the item order (NBE_BAND; 0: whole planes)
   bool wide16 = true;       // also for the 16-channel first layer (32-byte rows, SWIZZLE_32B row shifts; NBE_WIDE16)
   bool wide = true;         // w-halo'd activation blocks serving 9 taps per load (NBE_WIDE=0 disables)
@@ -266,7 +269,8 @@ int build_static(nbe_ctx* ctx) {
       bool ok = ctx->wide && vel;
       for (auto& p : s.parts) ok = ok && (p.type == T_CONV3 || p.type == T_SKIP1);
       if (!ok) continue;
-      if (s.inst == I_128_256_2) s.inst = ctx->dbuf ? I_PAIR_128_256_1 : (ctx->early ? I_EARLY_128_256_2 : I_PAIR_128_256_2);
+      if (s.inst == I_128_256_2)
+        s.inst = ctx->dbuf ? I_PAIR_128_256_1 : (ctx->f192 ? I_F192_2 : (ctx->early ? I_EARLY_128_256_2 : I_PAIR_128_256_2));
       else if (s.inst == I_256_512_1) s.inst = ctx->early ? I_EARLY_256_512_1 : I_PAIR_256_512_1;
       else if (s.inst == I_128_128_2) s.inst = I_PAIR_128_128_2;
       else if (s.inst == I_256_256_1) s.inst = I_PAIR_256_256_1;
@@ -338,6 +342,23 @@ int build_static(nbe_ctx* ctx) {
       } else if (ii.pair && k16) {   // N = 2C rows [Wh.. | dW]: CTA0 stages the primal rows, CTA1 the tangent rows
         prule(EMIT_WH, 0, 0, 0, C, 0, 0); prule(EMIT_WH, 0, 0, 0, C, 0, 3); prule(EMIT_WL, 0, 0, 0, C, 0, 6);
         prule(EMIT_DW, 0, 0, 1, C, 0, 0);
+      } else if (ii.f192 && !k16) {
+        // per-CTA stage (2C rows): rows [0, 1.5C) = this CTA's half of the N = 3C operand, rows [1.5C, 2C) = its half
+        // of Wh for dx * Wh.  kd 0 / 2 (and the folded 1^3 skip): [dW | Wl | Wh] -> (dy, ylo, y0); kd 1: [Wh | dW | Wl]
+        // -> (y1, dy, ylo).  lo stage: this CTA's half of Wh (xl * Wh -> y1).
+        auto xrule = [&](int what, int kind, int kdmask, int cta, int base, int o0, int o1) {
+          EmitRule& R = M.rules[nr++];
+          R.what = static_cast<int8_t>(what); R.kind = static_cast<int8_t>(kind); R.row_base = static_cast<int16_t>(base);
+          R.kcol = 0; R.alt_kd1 = 0; R.mod = 0; R.cta_base = static_cast<int8_t>(cta); R.kd_mask = static_cast<int8_t>(kdmask);
+          R.o_min = static_cast<int16_t>(o0); R.o_max = static_cast<int16_t>(o1);
+        };
+        const int H2 = C / 2;
+        xrule(EMIT_DW, 0, 0b101, 0, 0, 0, C);        xrule(EMIT_WL, 0, 0b101, 0, C, 0, H2);
+        xrule(EMIT_WL, 0, 0b101, 1, 0, H2, C);       xrule(EMIT_WH, 0, 0b101, 1, H2, 0, C);
+        xrule(EMIT_WH, 0, 0b010, 0, 0, 0, C);        xrule(EMIT_DW, 0, 0b010, 0, C, 0, H2);
+        xrule(EMIT_DW, 0, 0b010, 1, 0, H2, C);       xrule(EMIT_WL, 0, 0b010, 1, H2, 0, C);
+        xrule(EMIT_WH, 0, 0, 0, C + H2, 0, H2);      xrule(EMIT_WH, 0, 0, 1, C + H2, H2, C);      // dx * Wh halves
+        xrule(EMIT_WH, 1, 0, 0, 0, 0, H2);           xrule(EMIT_WH, 1, 0, 1, 0, H2, C);           // lo stage
       } else if (ii.pair && acc3) {
         // per-CTA stage rows: kd 0 / kd 1 [R0: C | R1: C/2], kd 2 [Wh half | dW half],
         // lo [Wl half | Wh half]; non-3^3 terms (folded skip) use the kd 0 form
@@ -448,6 +469,20 @@ int make_b_map16(nbe_ctx* ctx, CUtensorMap* m, const __half* base, int n_tiles, 
   return NBE_OK;
 }
 
+// 64-channel weight tiles as {64 ch, nrs rows, tiles}: one box = `box_rows` rows of three consecutive taps
+int make_b_map_lo3(nbe_ctx* ctx, CUtensorMap* m, const __half* base, int n_tiles, int nrs, int box_rows) {
+  if (n_tiles <= 0) { memset(m, 0, sizeof(*m)); return NBE_OK; }
+  cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(nrs), static_cast<cuuint64_t>(n_tiles)};
+  cuuint64_t str[2] = {128, static_cast<cuuint64_t>(nrs) * 128};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 3};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, str, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, NBE_ERR_CUDA, "cuTensorMapEncodeTiled(B lo3 tiles=%d) -> %d", n_tiles, (int)r);
+  return NBE_OK;
+}
+
 // ----------------------------------------------------------------------------------------
 // per-shape plan
 // ----------------------------------------------------------------------------------------
@@ -544,12 +579,16 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
       Lc.lo_rows = 0;
       memset(&Lc.bmap64_lo, 0, sizeof Lc.bmap64_lo);
       if (ctx->lo_box && ii.pair && ii.acc3 && s.n_tiles64 > 0) {
-        Lc.lo_rows = s.cout;
-        if ((rc = make_b_map(ctx, &Lc.bmap64_lo, packed + s.b64_off, 64, static_cast<long long>(s.n_tiles64) * ii.nrs, s.cout))) { delete P; return rc; }
+        Lc.lo_rows = ii.f192 ? s.cout / 2 : s.cout;
+        Lc.lo_taps = ii.f192 ? 3 : 1;
+        if (ii.f192) rc = make_b_map_lo3(ctx, &Lc.bmap64_lo, packed + s.b64_off, s.n_tiles64, ii.nrs, Lc.lo_rows);
+        else rc = make_b_map(ctx, &Lc.bmap64_lo, packed + s.b64_off, 64, static_cast<long long>(s.n_tiles64) * ii.nrs, Lc.lo_rows);
+        if (rc) { delete P; return rc; }
       }
 
       int ng = 0;
       bool bad = false;
+      const bool lo3 = ctx->lo_box && ii.f192;     // F192: a lo tap is 32 rows per CTA; three of them share a stage
       // lo-product groups are issued before the main groups (see conv_mma.cuh: truncating
       // accumulation), so collect them separately
       // main groups are further ordered by the accumulator they complete: kd 0 and the folded skip
@@ -570,10 +609,9 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
         const int C = ly.cout;
         const int tb = k16 ? p.tile_base16 : p.tile_base64;
         // OP(a, n8, b_row, d_col) -> device layout with byte offsets >> 4 precomputed
-        const int a_blk16 = ((16 * ii.tm + 2) * 10 * 128 + 1023) / 1024 * 1024 / 16;
         auto OP = [&](int a, int n8, int b_row, int d_col) {
           MmaOp o;
-          o.a_off = static_cast<uint16_t>(a * a_blk16);
+          o.a_off = static_cast<uint16_t>(a);
           o.b_off = static_cast<uint16_t>(b_row * (k16 ? 32 : 128) / 16);
           o.d_col = static_cast<uint16_t>(d_col);
           o.n8 = static_cast<uint8_t>(n8);
@@ -583,6 +621,18 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
         auto fill_ops = [&](GroupDesc& G, int kind, const Src& sc, int par, int kd) {
           const bool acc3 = ii.acc3 && !k16;
           const __half* ph = hi(sc.act);
+          if (ii.f192 && !k16) {
+            if (kind == 1) {      // lo phase: xl * Wh -> y1 (column 0)
+              G.n_a = 1; G.a_map[0] = static_cast<int16_t>(get_map(lo(sc.act), sc.act, par)); G.a_map[1] = -1; G.n_ops = 1;
+              G.ops[0] = OP(0, C / 8, 0, 0);
+            } else {              // xh * [..3C rows..] -> (dy, ylo, y0) or (y1, dy, ylo);  dx * Wh -> dy
+              G.n_a = 2; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par));
+              G.a_map[1] = static_cast<int16_t>(get_map(dx(sc.act), sc.act, par)); G.n_ops = 2;
+              G.ops[0] = OP(0, 3 * C / 8, 0, kd == 1 ? 0 : C);
+              G.ops[1] = OP(1, C / 8, C + C / 2, C);
+            }
+            return;
+          }
           if (ii.pair) {      // CTA-pair operand layout (see build_static): b_row is a row of the per-CTA stage
             G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par));
             if (k16) {
@@ -682,9 +732,14 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           G.ntaps = static_cast<int8_t>(ntaps); G.kc16 = k16 ? 1 : 0; G.c0 = static_cast<int16_t>(sc.c0);
           G.dw = static_cast<int8_t>(sc.crop + p.off + dw_); G.dh = static_cast<int8_t>(sc.crop + p.off + dh_);
           G.dd = static_cast<int8_t>(sc.crop + p.off + dd_);
-          G.brow0 = tile0 * ii.nrs; G.brow_step = ii.nrs;
+          G.brow0 = tile0 * ii.nrs; G.brow_step = static_cast<int16_t>(ii.nrs);
+          G.tap_rows = static_cast<int16_t>(ii.pair ? ii.nrs / 2 : ii.nrs);
           G.pitch = static_cast<int8_t>(ntaps == 9 ? 10 : 8);
           G.tps = static_cast<int8_t>((k16 && ntaps >= 3) ? 3 : 1);
+          if (!k16 && kind == 1 && lo3) {                              // three lo taps per weight stage
+            if (ntaps == 9) G.tps = 3;
+            G.tap_rows = static_cast<int16_t>(s.cout / 2);
+          }
           cur_box_w = G.pitch;
           cur_kind = k16 ? 0 : kind;
           cur_kd = (ii.acc3 && !k16 && kd > 0) ? kd : 0;
@@ -720,7 +775,16 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           H.flops += 2.0 * ly.cout * ly.cin * vout * m;
         }
       }
-      if (ii.early) {
+      if (ii.f192) {
+        if (g_lo.empty() || g_main[0].empty() || g_main[1].empty() || g_main[2].empty()) bad = true;
+        else {
+          g_lo.front().pre_wait = 3;            // lo phase accumulates into y1 (drained during the previous item's kd 2)
+          g_main[0].front().pre_wait = 2;       // first MMA touching (dy, ylo, y0)
+          g_main[0].back().post_sig = 1;        // y0 complete
+          g_main[1].back().post_sig = 2;        // y1 complete
+          g_main[2].front().pre_wait = 1;       // kd 2 re-uses the y0 columns: drained and re-zeroed first
+        }
+      } else if (ii.early) {
         if (g_lo.empty() || g_main[0].empty() || g_main[1].empty() || g_main[2].empty()) bad = true;
         else {
           g_lo.front().pre_wait = 1;            // lo products accumulate into y0
@@ -793,7 +857,7 @@ cudaError_t launch_inst(int device, const ConvLaunch* dl, const GroupTable& gt, 
   return cudaGetLastError();
 }
 
-template <int NRS, int DC, int TM, bool EARLY = false>
+template <int NRS, int DC, int TM, int EARLY = 0>
 cudaError_t launch_pair(int device, const ConvLaunch* dl, const GroupTable& gt, const FinalArgs& fa, int grid, cudaStream_t st) {
   using Cfg = ConvCfg<NRS, DC, TM, true>;
   static std::atomic<uint64_t> done{0};
@@ -824,8 +888,9 @@ cudaError_t launch_conv(int device, int inst, const ConvLaunch* dl, const GroupT
     case I_PAIR_128_128_2: return launch_pair<192, 128, 2>(device, dl, gt, fa, grid, st);
     case I_PAIR_256_256_1: return launch_pair<384, 256, 1>(device, dl, gt, fa, grid, st);
     case I_PAIR_128_256_1: return launch_pair<192, 256, 1>(device, dl, gt, fa, grid, st);
-    case I_EARLY_128_256_2: return launch_pair<192, 256, 2, true>(device, dl, gt, fa, grid, st);
-    case I_EARLY_256_512_1: return launch_pair<384, 512, 1, true>(device, dl, gt, fa, grid, st);
+    case I_EARLY_128_256_2: return launch_pair<192, 256, 2, 1>(device, dl, gt, fa, grid, st);
+    case I_EARLY_256_512_1: return launch_pair<384, 512, 1, 1>(device, dl, gt, fa, grid, st);
+    case I_F192_2: return launch_pair<256, 256, 2, 2>(device, dl, gt, fa, grid, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -1018,6 +1083,7 @@ int nbe_create(nbe_ctx** out, int device) {
   if (const char* e = getenv("NBE_DBUF")) ctx->dbuf = atoi(e) != 0;
   if (const char* e = getenv("NBE_EARLY")) ctx->early = atoi(e) != 0;
   if (const char* e = getenv("NBE_LOBOX")) ctx->lo_box = atoi(e) != 0;
+  if (const char* e = getenv("NBE_F192")) ctx->f192 = atoi(e) != 0;
   if (const char* e = getenv("NBE_WIDE16")) ctx->wide16 = atoi(e) != 0;
   if (const char* e = getenv("NBE_BAND")) ctx->band_h = atoi(e);
   cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
