@@ -56,6 +56,9 @@ struct LayerMeta {
   int tap_tile[27];
   EmitRule rules[kMaxRules];
   int pair_rows;         // rows per CTA in a pair-layout stage
+  // accumulation chains (conv_mma.cuh, EARLY == 3): kd_mask of a rule selects by the PHASE of the 3-tap
+  // block a tap belongs to, phase = (chain_par0 + kd * chain_nkc + kc + kw) & 1
+  int chain, chain_par0, chain_nkc;
 };
 
 __global__ void __launch_bounds__(128)
@@ -139,7 +142,8 @@ modulate_kernel(const LayerMeta* __restrict__ metas, int n_layers, const float* 
       const long long tile = M.tap_tile[tap] + kc * M.kc_stride + R.kind * M.kind_stride;
       const int col = M.kc16 ? (R.kcol + i) : (i & 63);
       const int kd = M.k3 == 27 ? tap / 9 : 0;
-      if (R.kd_mask && !((R.kd_mask >> kd) & 1)) continue;
+      const int sel = M.chain ? ((M.chain_par0 + kd * M.chain_nkc + kc + (M.k3 == 27 ? tap % 3 : 0)) & 1) : kd;
+      if (R.kd_mask && !((R.kd_mask >> sel) & 1)) continue;
       if (R.o_max > 0 && (o < R.o_min || o >= R.o_max)) continue;
       const int row = R.o_max > 0 ? (R.cta_base * M.pair_rows + R.row_base + (o - R.o_min))
                       : R.mod ? ((o / R.mod + R.cta_base) * M.pair_rows + R.row_base + o % R.mod)

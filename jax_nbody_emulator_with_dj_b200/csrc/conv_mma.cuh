@@ -55,6 +55,11 @@ struct GroupDesc {
   int32_t brow0;      // B row of tap 0
   int16_t brow_step;  // B rows between consecutive taps
   int16_t tap_rows;   // rows between consecutive taps INSIDE a multi-tap weight stage (this CTA's rows per tap)
+  // EARLY == 3 (accumulation chains): the group's taps are cut into blocks of 3; block b accumulates into
+  // primal accumulator (phase0 + b) & 1 (0: y0, 1: y1), which is handed to the epilogue after the block
+  int8_t chain;
+  int8_t phase0;
+  int8_t pad_[2];
   MmaOp ops[3];
 };
 
@@ -74,6 +79,7 @@ struct alignas(128) ConvLaunch {
                             // lo_taps == 3: a 3-D map {64, rows, tiles} whose box carries three consecutive taps
   int32_t lo_rows;          // rows per CTA of a lo stage (0: lo stages use bmap64)
   int32_t lo_taps;          // taps per lo-stage box: 1 or 3
+  int32_t n_chains;         // EARLY == 3: accumulation chains per item (1 lo chain + the 3-tap blocks of the main groups)
   int32_t n_par;            // 1, or 8 for the x2 up-sampling conv (one parity per item)
   int32_t par_brow_step;    // B rows between parities
   int32_t out_w, out_h, out_d;         // extent of the tile space
@@ -182,6 +188,17 @@ constexpr bool kBaseOffsetMode = NBE_BASE_OFFSET != 0;
 // y0 (then y1) while kd 1 (kd 2) runs, the issuers wait for y0_empty before kd 2, and the next item's
 // lo phase needs only y1 (drained during kd 2), so the end-of-item drain of (dy, ylo, y0') hides under it.
 // Sum order ((y0 + y1) + y0') + ylo.
+//
+// EARLY == 3 ("chains", same instance and column layout as F192): the tensor core TRUNCATES when it adds
+// into the fp32 accumulator, a systematic relative shrink that grows with the number of accumulations
+// into one column.  Here the two primal accumulators are used in turn: the lo
+// phase (xl * Wh, all taps) is one chain into y1, then every block of three taps of the main groups
+// (12 accumulations) goes to y0 / y1 alternately, with the weight rows of a tap ordered for the
+// accumulator its block uses ([dW | Wl | Wh] -> (dy, ylo, y0), [Wh | dW | Wl] -> (y1, dy, ylo)).  After each
+// chain the issuers commit y?_full, the epilogue (idle 80 % of the time) adds the 64 columns to its
+// register sum with round-to-nearest adds, re-zeroes them and arrives on y?_empty, which the issuers
+// wait on before the next chain into the same accumulator -- one whole block later.  dy and ylo
+// accumulate through the item as before.
 template <int NRS, int DC, int TM, bool FINAL, bool PAIR = false, int EARLY = 0>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupTable gt,
@@ -206,7 +223,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
   uint64_t* y1_empty = y0_empty + 1;       // EARLY == 2 only
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y1_empty + 1);
   static_assert(EARLY == 0 || (Cfg::kNBuf == 1 && !FINAL && TM * DC == 512), "EARLY: single-stage acc3 instances only");
-  static_assert(EARLY != 2 || (PAIR && TM == 2 && DC == 256), "F192: 64-output pair instance only");
+  static_assert(EARLY < 2 || (PAIR && TM == 2 && DC == 256), "F192: 64-output pair instance only");
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);   // up to 128 floats
 
   const int warp = threadIdx.x >> 5;
@@ -389,6 +406,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     constexpr uint32_t idesc_base = umma_idesc_f16(PAIR ? 256 : 128, 0, false);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0, buf = 0, pacc = 0;
+    uint32_t pe = 0;      // EARLY == 3: bit a = parity of the next wait on y<a>_empty
     for (long long item = item_first; item < n_items && (!PAIR || rank == 0); item += gridDim.x) {
       if constexpr (EARLY == 0) {
         mbar_wait(&acc_empty[buf], pacc ^ 1);
@@ -402,7 +420,11 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
           // pre_wait 1: y0_empty, 2: acc_empty, 3: y1_empty.  All are signalled by the PREVIOUS item's
           // epilogue, except y0_empty in the F192 layout, which kd 2 needs from the CURRENT item
           const int pw = G.pre_wait;
-          if (pw != 0) {
+          if (EARLY == 3 && pw == 3) {            // start of the lo chain (into y1)
+            mbar_wait(y1_empty, ((pe >> 1) & 1u) ^ 1u);
+            pe ^= 2u;
+            tc_fence_after();
+          } else if (pw != 0) {
             uint64_t* bar = pw == 1 ? y0_empty : (pw == 2 ? &acc_empty[0] : y1_empty);
             mbar_wait(bar, (EARLY == 2 && pw == 1) ? pacc : (pacc ^ 1));
             tc_fence_after();
@@ -474,6 +496,22 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
           }
         } else
         for (int j = 0, jt = 0; j < ntaps; ++j) {
+          // EARLY == 3: block j / 3 of a chain group accumulates into y0 (phase 0) or y1 (phase 1); the
+          // accumulator must have been drained since its previous chain
+          uint32_t chain_p = 0u, d_sel = op_d[0];
+          bool chain_end = false;
+          if constexpr (EARLY == 3) {
+            if (G.chain != 0) {
+              chain_p = (static_cast<uint32_t>(G.phase0) + static_cast<uint32_t>(j) / 3u) & 1u;
+              if (j % 3 == 0) {
+                mbar_wait(chain_p ? y1_empty : y0_empty, ((pe >> chain_p) & 1u) ^ 1u);
+                pe ^= (1u << chain_p);
+                tc_fence_after();
+              }
+              d_sel = chain_p ? 0u : op_d[0];
+              chain_end = (j % 3 == 2) || (j == ntaps - 1);
+            }
+          }
           if (jt == 0) {
             mbar_wait(&b_full[sb], pb);
             tc_fence_after();
@@ -505,13 +543,16 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
 #pragma unroll
                   for (int o = 0; o < 3; ++o)
                     if (o < n_ops)
-                      mma(d_tile + op_d[o],
+                      mma(d_tile + (o == 0 ? d_sel : op_d[o]),
                           (static_cast<uint64_t>(a_hi) << 32) | (op_a[o] + a_row + 2u * k),
                           (static_cast<uint64_t>(bdesc_hi) << 32) | (b_lo + op_b[o] + 2u * k), op_i[o], 1u);
                 }
               }
             }
             if (jt == tps - 1) commit(&b_empty[sb]);
+            if constexpr (EARLY == 3) {
+              if (chain_end) commit(chain_p ? y1_full : y0_full);
+            }
           }
           __syncwarp();
           if (++jt == tps) {
@@ -561,8 +602,10 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
       // thread owns row r of tile t and the two 32-channel chunks ch(0), ch(1) (TM == 1: the warp sets
       // take alternate chunks of the 128)
       constexpr int COUT = DC / 4;
-      constexpr int cY0 = EARLY == 2 ? 3 * COUT : 0;          // first primal accumulator to complete
-      constexpr int cY1 = EARLY == 2 ? 0 : 2 * COUT;          // second
+      constexpr int cY0 = EARLY >= 2 ? 3 * COUT : 0;          // first primal accumulator to complete
+      constexpr int cY1 = EARLY >= 2 ? 0 : 2 * COUT;          // second
+      uint32_t pf = 0;                                        // EARLY == 3: bit a = parity of the next wait on y<a>_full
+      const int n_chains = L->n_chains;
       constexpr int cYZ = 3 * COUT;                           // last: y2, or y0 re-used by kd 2
       constexpr int cDY = COUT;
       constexpr int cLO = 2 * COUT;                           // F192 only: xh * Wl
@@ -582,6 +625,36 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
         const int h = h0 + t * 16 + (r >> 3);
         const bool valid = item_ok && (w < out_w) && (h < out_h);
         uint32_t ps[64];
+        if constexpr (EARLY == 3) {
+          // accumulation chains: chain 0 (lo phase) comes back in y1, chain c >= 1 in y0 / y1 alternately
+#pragma unroll
+          for (int k = 0; k < 64; ++k) ps[k] = 0u;
+          for (int cn = 0; cn < n_chains; ++cn) {
+            const uint32_t a = cn == 0 ? 1u : (static_cast<uint32_t>(cn - 1) & 1u);
+            mbar_wait(a ? y1_full : y0_full, (pf >> a) & 1u);
+            pf ^= (1u << a);
+            tc_fence_after();
+            if (!dead) {
+              // both chunks in flight at once: the drain is latency-bound and sits on the issuers' critical
+              // path (the next chain into this accumulator waits for it)
+              const uint32_t col = taddr + (a ? cY1 : cY0);
+              uint32_t yv[64];
+              tmem_ld32(col + ch(0), yv);
+              tmem_ld32(col + ch(1), yv + 32);
+              tmem_ld_wait();
+              tmem_st32_zero(col + ch(0));
+              tmem_st32_zero(col + ch(1));
+              tmem_st_wait();
+              tc_fence_before();
+              arrive(a ? y1_empty : y0_empty);      // hand the columns back before the register adds
+#pragma unroll
+              for (int j = 0; j < 64; ++j) ps[j] = __float_as_uint(__uint_as_float(ps[j]) + __uint_as_float(yv[j]));
+            } else {
+              tc_fence_before();
+              arrive(a ? y1_empty : y0_empty);
+            }
+          }
+        } else {
         // ---- y0: complete once the kd = 0 groups are done (two more kd-planes of MMAs still to come)
         mbar_wait(y0_full, pacc);
         tc_fence_after();
@@ -615,6 +688,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
           tc_fence_before();
           arrive(y1_empty);                       // the next item's lo phase (xl * Wh -> y1) may start
         }
+        }
         // ---- last primal accumulator, dy (and ylo): end of the item
         mbar_wait(&acc_full[0], pacc);
         tc_fence_after();
@@ -627,19 +701,23 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
             for (int hf = 0; hf < 2; ++hf) {
               const int c = ch(i) + 16 * hf;
               uint32_t y2[16], dy[16], yl[16];
-              tmem_ld16(taddr + cYZ + c, y2);
+              if constexpr (EARLY != 3) tmem_ld16(taddr + cYZ + c, y2);
               tmem_ld16(taddr + cDY + c, dy);
-              if constexpr (EARLY == 2) tmem_ld16(taddr + cLO + c, yl);
+              if constexpr (EARLY >= 2) tmem_ld16(taddr + cLO + c, yl);
               tmem_ld_wait();
-              tmem_st16_zero(taddr + cYZ + c);
+              if constexpr (EARLY != 3) tmem_st16_zero(taddr + cYZ + c);
               tmem_st16_zero(taddr + cDY + c);
-              if constexpr (EARLY == 2) tmem_st16_zero(taddr + cLO + c);
+              if constexpr (EARLY >= 2) tmem_st16_zero(taddr + cLO + c);
               uint32_t ph[8], pl[8], pd[8];
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
-                float s0 = __uint_as_float(ps[32 * i + 16 * hf + j]) + __uint_as_float(y2[j]);
-                float s1 = __uint_as_float(ps[32 * i + 16 * hf + j + 1]) + __uint_as_float(y2[j + 1]);
-                if constexpr (EARLY == 2) {
+                float s0 = __uint_as_float(ps[32 * i + 16 * hf + j]);
+                float s1 = __uint_as_float(ps[32 * i + 16 * hf + j + 1]);
+                if constexpr (EARLY != 3) {
+                  s0 += __uint_as_float(y2[j]);
+                  s1 += __uint_as_float(y2[j + 1]);
+                }
+                if constexpr (EARLY >= 2) {
                   s0 += __uint_as_float(yl[j]);
                   s1 += __uint_as_float(yl[j + 1]);
                 }

@@ -31,8 +31,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 enum ConvType { T_CONV3 = 0, T_SKIP1 = 1, T_DOWN = 2, T_UP = 3 };
-enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_PAIR_256_512_1, I_PAIR_128_128_2, I_PAIR_256_256_1, I_PAIR_128_256_1, I_EARLY_128_256_2, I_EARLY_256_512_1, I_F192_2, I_COUNT };
-struct InstInfo { int nrs, dc, tm; bool fin; bool pair = false; bool acc3 = false; bool early = false; bool f192 = false; };
+enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_PAIR_256_512_1, I_PAIR_128_128_2, I_PAIR_256_256_1, I_PAIR_128_256_1, I_EARLY_128_256_2, I_EARLY_256_512_1, I_F192_2, I_CHAIN_2, I_COUNT };
+struct InstInfo { int nrs, dc, tm; bool fin; bool pair = false; bool acc3 = false; bool early = false; bool f192 = false; bool chain = false; };
 const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32, 16, 2, true},
                                  {128, 64, 2, false},  {64, 64, 2, false},   {256, 128, 1, false},
                                  {128, 256, 2, false, false, true}, {256, 512, 1, false, false, true},
@@ -44,7 +44,9 @@ const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32
                                  // early-drain acc3 pair instances (fine-grained accumulator hand-over, conv_mma.cuh)
                                  {192, 256, 2, false, true, true, true}, {384, 512, 1, false, true, true, true},
                                  // F192: N = 192 fused [Wh|dW|Wl] main product, 2 x 128 weight rows per stage (conv_mma.cuh, EARLY == 2)
-                                 {256, 256, 2, false, true, true, true, true}};
+                                 {256, 256, 2, false, true, true, true, true},
+                                 // F192 + accumulation chains (EARLY == 3): the two primal accumulators alternate every 3 taps
+                                 {256, 256, 2, false, true, true, true, true, true}};
 
 // activation tensors of the net
 enum ActId {
@@ -115,6 +117,7 @@ struct nbe_ctx {
   bool early = true;        // acc3 pair launches hand the per-kd accumulators over as they complete (NBE_EARLY=0: whole item)
   bool lo_box = true;       // lo-product weight stages are loaded with a box of only the rows they use (NBE_LOBOX=0)
   bool f192 = true;         // 64-output acc3 pair launches use the N = 192 fused instance (NBE_F192=0: EARLY / plain)
+  bool chain = true;        // ... with accumulation chains of 3 taps (NBE_CHAIN=0: one chain per kd-plane)
   int band_h = 2;           // tile rows per h-band of the item order (NBE_BAND; 0: whole planes)
   bool wide16 = true;       // also for the 16-channel first layer (32-byte rows, SWIZZLE_32B row shifts; NBE_WIDE16)
   bool wide = true;         // w-halo'd activation blocks serving 9 taps per load (NBE_WIDE=0 disables)
@@ -270,7 +273,8 @@ int build_static(nbe_ctx* ctx) {
       for (auto& p : s.parts) ok = ok && (p.type == T_CONV3 || p.type == T_SKIP1);
       if (!ok) continue;
       if (s.inst == I_128_256_2)
-        s.inst = ctx->dbuf ? I_PAIR_128_256_1 : (ctx->f192 ? I_F192_2 : (ctx->early ? I_EARLY_128_256_2 : I_PAIR_128_256_2));
+        s.inst = ctx->dbuf ? I_PAIR_128_256_1
+                 : (ctx->f192 ? (ctx->chain ? I_CHAIN_2 : I_F192_2) : (ctx->early ? I_EARLY_128_256_2 : I_PAIR_128_256_2));
       else if (s.inst == I_256_512_1) s.inst = ctx->early ? I_EARLY_256_512_1 : I_PAIR_256_512_1;
       else if (s.inst == I_128_128_2) s.inst = I_PAIR_128_128_2;
       else if (s.inst == I_256_256_1) s.inst = I_PAIR_256_256_1;
@@ -353,8 +357,11 @@ int build_static(nbe_ctx* ctx) {
           R.o_min = static_cast<int16_t>(o0); R.o_max = static_cast<int16_t>(o1);
         };
         const int H2 = C / 2;
-        xrule(EMIT_DW, 0, 0b101, 0, 0, 0, C);        xrule(EMIT_WL, 0, 0b101, 0, C, 0, H2);
-        xrule(EMIT_WL, 0, 0b101, 1, 0, H2, C);       xrule(EMIT_WH, 0, 0b101, 1, H2, 0, C);
+        // kd masks 0b101 / 0b010; with accumulation chains the same two row orders are selected by the phase of
+        // the tap's 3-tap block instead (bit 0: y0 side, bit 1: y1 side), see LayerMeta::chain
+        const int m0 = ii.chain ? 0b01 : 0b101;
+        xrule(EMIT_DW, 0, m0, 0, 0, 0, C);           xrule(EMIT_WL, 0, m0, 0, C, 0, H2);
+        xrule(EMIT_WL, 0, m0, 1, 0, H2, C);          xrule(EMIT_WH, 0, m0, 1, H2, 0, C);
         xrule(EMIT_WH, 0, 0b010, 0, 0, 0, C);        xrule(EMIT_DW, 0, 0b010, 0, C, 0, H2);
         xrule(EMIT_DW, 0, 0b010, 1, 0, H2, C);       xrule(EMIT_WL, 0, 0b010, 1, H2, 0, C);
         xrule(EMIT_WH, 0, 0, 0, C + H2, 0, H2);      xrule(EMIT_WH, 0, 0, 1, C + H2, H2, C);      // dx * Wh halves
@@ -382,6 +389,15 @@ int build_static(nbe_ctx* ctx) {
         if (split) rule(EMIT_WL, 0, C, 0);
       }
       M.n_rules = nr;
+      M.chain = (ii.chain && !k16) ? 1 : 0;
+      M.chain_nkc = nkc;
+      M.chain_par0 = 0;
+      if (M.chain && p.type == T_CONV3) {
+        // blocks are numbered in launch order: the folded 64-channel skip's one-tap blocks first, then the
+        // 3-tap blocks of (kd, kc, kw); a 16-channel skip belongs to the lo chain and has no block
+        for (auto& p2 : s.parts)
+          if (p2.type == T_SKIP1 && !p2.src[0].kc16) M.chain_par0 = static_cast<int>(p2.src.size()) & 1;
+      }
     }
     s.n_tiles64 = t64; s.n_tiles16 = t16;
     s.b64_off = off; off += static_cast<long long>(t64) * ii.nrs * 64;
@@ -594,9 +610,14 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
       // main groups are further ordered by the accumulator they complete: kd 0 and the folded skip
       // (y0, dy) | kd 1 (dy, y1) | kd 2 (y2, dy), which is what lets the EARLY instances drain y0 / y1
       // while later kd-planes are still running
-      std::vector<GroupDesc> g_lo, g_main[3];
-      int cur_kind = 0, cur_kd = 0;
-      auto push = [&](const GroupDesc& G) { (cur_kind == 1 ? g_lo : g_main[cur_kd]).push_back(G); };
+      std::vector<GroupDesc> g_lo, g_main[3], g_skip16, g_skip64;   // the skip lists are used by the chain instance only
+      int cur_kind = 0, cur_kd = 0, cur_skip = 0;
+      auto push = [&](const GroupDesc& G) {
+        if (cur_kind == 1) g_lo.push_back(G);
+        else if (ii.chain && cur_skip == 1) g_skip16.push_back(G);
+        else if (ii.chain && cur_skip == 2) g_skip64.push_back(G);
+        else g_main[cur_kd].push_back(G);
+      };
       const int nkind = (vel && split) ? 2 : 1;
       const ActBuf& OB = P->act[s.out_act];
       // tile space = output voxels, except for the up-sampling conv (input voxels)
@@ -628,7 +649,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
             } else {              // xh * [..3C rows..] -> (dy, ylo, y0) or (y1, dy, ylo);  dx * Wh -> dy
               G.n_a = 2; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par));
               G.a_map[1] = static_cast<int16_t>(get_map(dx(sc.act), sc.act, par)); G.n_ops = 2;
-              G.ops[0] = OP(0, 3 * C / 8, 0, kd == 1 ? 0 : C);
+              G.ops[0] = OP(0, 3 * C / 8, 0, (kd == 1 && !ii.chain) ? 0 : C);      // chains: the kernel picks 0 / C per 3-tap block
               G.ops[1] = OP(1, C / 8, C + C / 2, C);
             }
             return;
@@ -743,6 +764,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           cur_box_w = G.pitch;
           cur_kind = k16 ? 0 : kind;
           cur_kd = (ii.acc3 && !k16 && kd > 0) ? kd : 0;
+          cur_skip = p.type == T_SKIP1 ? (k16 ? 1 : 2) : 0;
           G.lo_stage = (cur_kind == 1) ? 1 : 0;
           fill_ops(G, kind, sc, par, kd);
           if (G.a_map[0] < 0 || (G.n_a == 2 && G.a_map[1] < 0)) bad = true;
@@ -775,7 +797,30 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           H.flops += 2.0 * ly.cout * ly.cin * vout * m;
         }
       }
-      if (ii.f192) {
+      Lc.n_chains = 0;
+      if (ii.chain) {
+        // accumulation chains (conv_mma.cuh, EARLY == 3).  Chain 0 = the lo phase (+ a 16-channel folded skip,
+        // whose fixed operand layout writes (y1, dy)) into y1; then the 64-channel skip's one-tap blocks and the
+        // 3-tap blocks of the conv groups, alternating y0 / y1 starting with y0.
+        if (g_lo.empty() || g_main[0].empty() || g_main[1].empty() || g_main[2].empty()) bad = true;
+        else {
+          g_lo.front().pre_wait = 3;
+          if (!g_skip16.empty()) { g_skip16.front().pre_wait = 2; g_skip16.back().post_sig = 2; }
+          else g_lo.back().post_sig = 2;
+          g_lo.insert(g_lo.end(), g_skip16.begin(), g_skip16.end());
+          int blk = 0;
+          std::vector<GroupDesc> mains;
+          mains.insert(mains.end(), g_skip64.begin(), g_skip64.end());
+          for (int kq = 0; kq < 3; ++kq) { mains.insert(mains.end(), g_main[kq].begin(), g_main[kq].end()); g_main[kq].clear(); }
+          mains.front().pre_wait = 2;             // first MMA touching dy / ylo / y0 of this item
+          for (auto& G : mains) {
+            G.chain = 1; G.phase0 = static_cast<int8_t>(blk & 1);
+            blk += (G.ntaps + 2) / 3;
+          }
+          g_main[0] = mains;
+          Lc.n_chains = 1 + blk;
+        }
+      } else if (ii.f192) {
         if (g_lo.empty() || g_main[0].empty() || g_main[1].empty() || g_main[2].empty()) bad = true;
         else {
           g_lo.front().pre_wait = 3;            // lo phase accumulates into y1 (drained during the previous item's kd 2)
@@ -891,6 +936,7 @@ cudaError_t launch_conv(int device, int inst, const ConvLaunch* dl, const GroupT
     case I_EARLY_128_256_2: return launch_pair<192, 256, 2, 1>(device, dl, gt, fa, grid, st);
     case I_EARLY_256_512_1: return launch_pair<384, 512, 1, 1>(device, dl, gt, fa, grid, st);
     case I_F192_2: return launch_pair<256, 256, 2, 2>(device, dl, gt, fa, grid, st);
+    case I_CHAIN_2: return launch_pair<256, 256, 2, 3>(device, dl, gt, fa, grid, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -1084,6 +1130,7 @@ int nbe_create(nbe_ctx** out, int device) {
   if (const char* e = getenv("NBE_EARLY")) ctx->early = atoi(e) != 0;
   if (const char* e = getenv("NBE_LOBOX")) ctx->lo_box = atoi(e) != 0;
   if (const char* e = getenv("NBE_F192")) ctx->f192 = atoi(e) != 0;
+  if (const char* e = getenv("NBE_CHAIN")) ctx->chain = atoi(e) != 0;
   if (const char* e = getenv("NBE_WIDE16")) ctx->wide16 = atoi(e) != 0;
   if (const char* e = getenv("NBE_BAND")) ctx->band_h = atoi(e);
   cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
