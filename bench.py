@@ -582,6 +582,8 @@ def main():
             hostbar = dist.new_group(backend="gloo")
             del box_dev, disp_dev, vel_dev
             torch.cuda.empty_cache()
+            if rank != 0:
+                eng.release_workspace()       # rank 0 is about to run its own context on this GPU
             dist.barrier(group=hostbar)
         if rank == 0:
             devs = list(range(world))

@@ -173,6 +173,10 @@ int nbe_pk_bins(nbe_ctx* ctx, const void* delta_k_dev, int32_t res, int32_t mas_
  * of boxsize when delta_k is the unnormalised forward FFT and the inverse is normalised.       */
 int nbe_za_psi_k(nbe_ctx* ctx, const void* delta_k_dev, int32_t res, float boxsize, void* psi_k_dev, void* stream);
 
+/* Free the activation arena, cached plans and box staging buffers of the context (re-created on demand;
+ * parameters and packed weights stay): for processes that share a GPU or alternate between shapes.   */
+int nbe_release_workspace(nbe_ctx* ctx);
+
 /* Bytes of device memory the context needs for one (n0,n1,n2) sample (activation arena). */
 size_t nbe_workspace_bytes(nbe_ctx* ctx, const int32_t dims[3]);
 

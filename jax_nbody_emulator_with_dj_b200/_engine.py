@@ -312,5 +312,9 @@ class Engine:
         n = self.lib.nbe_get_profile(self.h, cap, names, ms, fl)
         return [(names[i].decode(), float(ms[i]), float(fl[i])) for i in range(min(n, cap))]
 
+    def release_workspace(self):
+        """Free the activation arena / plans / staging buffers (re-created on demand)."""
+        self._ck(self.lib.nbe_release_workspace(self.h))
+
     def workspace_bytes(self, dims):
         return int(self.lib.nbe_workspace_bytes(self.h, (C.c_int32 * 3)(*dims)))

@@ -23,7 +23,7 @@ EXPORTS = (
     "nbe_create", "nbe_destroy", "nbe_last_error", "nbe_version", "nbe_set_params", "nbe_set_precision",
     "nbe_modulate", "nbe_get_modulated", "nbe_forward", "nbe_process_box", "nbe_process_box_dev",
     "nbe_process_box_multi", "nbe_process_box_blocks",
-    "nbe_workspace_bytes", "nbe_host_register", "nbe_host_unregister",
+    "nbe_workspace_bytes", "nbe_release_workspace", "nbe_host_register", "nbe_host_unregister",
     "nbe_launch_count", "nbe_set_profiling", "nbe_get_profile", "nbe_debug_read_act",
     "nbe_density_from_psi", "nbe_mas_deconvolve", "nbe_pk_bins", "nbe_za_psi_k",
 )
@@ -97,6 +97,7 @@ def load():
         lib.nbe_mas_deconvolve.argtypes = [vp, vp, C.c_int32, C.c_int32, vp]
         lib.nbe_pk_bins.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp]
         lib.nbe_za_psi_k.argtypes = [vp, vp, C.c_int32, C.c_float, vp, vp]
+        lib.nbe_release_workspace.argtypes = [vp]
         lib.nbe_workspace_bytes.argtypes = [vp, i32p]
         lib.nbe_workspace_bytes.restype = C.c_size_t
         lib.nbe_launch_count.argtypes = [vp, C.c_int]

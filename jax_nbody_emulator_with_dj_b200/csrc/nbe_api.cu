@@ -117,6 +117,8 @@ struct nbe_ctx {
   bool early = true;        // acc3 pair launches hand the per-kd accumulators over as they complete (NBE_EARLY=0: whole item)
   bool lo_box = true;       // lo-product weight stages are loaded with a box of only the rows they use (NBE_LOBOX=0)
   bool f192 = true;         // 64-output acc3 pair launches use the N = 192 fused instance (NBE_F192=0: EARLY / plain)
+  bool trace = false;       // NBE_TRACE=1: upload timings on stderr (synchronises the upload stream: not for benchmarks)
+  bool w_window = true;     // the first subbox's upload is windowed in W as well (NBE_WWIN=0: whole rows)
   bool chain = true;        // ... with accumulation chains of 3 taps (NBE_CHAIN=0: one chain per kd-plane)
   int band_h = 2;           // tile rows per h-band of the item order (NBE_BAND; 0: whole planes)
   bool wide16 = true;       // also for the 16-channel first layer (32-byte rows, SWIZZLE_32B row shifts; NBE_WIDE16)
@@ -1131,6 +1133,8 @@ int nbe_create(nbe_ctx** out, int device) {
   if (const char* e = getenv("NBE_LOBOX")) ctx->lo_box = atoi(e) != 0;
   if (const char* e = getenv("NBE_F192")) ctx->f192 = atoi(e) != 0;
   if (const char* e = getenv("NBE_CHAIN")) ctx->chain = atoi(e) != 0;
+  if (const char* e = getenv("NBE_WWIN")) ctx->w_window = atoi(e) != 0;
+  if (const char* e = getenv("NBE_TRACE")) ctx->trace = atoi(e) != 0;
   if (const char* e = getenv("NBE_WIDE16")) ctx->wide16 = atoi(e) != 0;
   if (const char* e = getenv("NBE_BAND")) ctx->band_h = atoi(e);
   cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
@@ -1429,24 +1433,41 @@ static int process_box_host(nbe_ctx* ctx, const void* in_host, int in_dtype, con
   std::vector<cudaEvent_t> up_ev(static_cast<size_t>(sub_count), nullptr);
   auto destroy_events = [&]() { for (auto e : up_ev) if (e) cudaEventDestroy(e); };
   {
-    std::vector<uint8_t> have(static_cast<size_t>(nD * nH), 0);
-    typedef std::vector<std::pair<int32_t, int32_t>> Runs;       // (first H slot, count)
+    // W is windowed as well, in blocks of WB columns (<= 64 blocks, one bit each): the first subbox then
+    // waits for 224 x 224 x 256 instead of 224 x 224 x 512 voxels per channel.  The device rows keep the
+    // full width (the W tables are not remapped), only the transfers are narrower.
+    const int64_t WB = ctx->w_window ? std::max<int64_t>(32, (S2 + 63) / 64) : S2;
+    const int nWB = static_cast<int>((S2 + WB - 1) / WB);
+    const uint64_t all_w = nWB >= 64 ? ~0ull : ((1ull << nWB) - 1ull);
+    std::vector<uint64_t> have(static_cast<size_t>(nD * nH), 0ull);
+    struct Run { int32_t h0, n; uint64_t mask; bool operator==(const Run& o) const { return h0 == o.h0 && n == o.n && mask == o.mask; } };
+    typedef std::vector<Run> Runs;
+    // Only the FIRST subbox of the call is W-windowed (it is the one transfer nothing hides); every later
+    // unit brings whole rows, or the rest of a partly present row, in large strided copies.
+    const size_t cmp_n = static_cast<size_t>(plen[0] + plen[1]);
+    cudaEvent_t tr0 = nullptr;
+    if (ctx->trace) { cudaEventCreate(&tr0); cudaEventRecord(tr0, us); }
     for (int u0 = 0; u0 < sub_count;) {
       int u1 = u0;
-      while (u1 + 1 < sub_count && memcmp(&tabs_src[static_cast<size_t>(u1 + 1) * per], &tabs_src[static_cast<size_t>(u0) * per],
-                                         sizeof(int32_t) * (plen[0] + plen[1])) == 0) ++u1;
+      const bool first_win = ctx->w_window && u0 == 0;
+      while (!first_win && u1 + 1 < sub_count &&
+             memcmp(&tabs_src[static_cast<size_t>(u1 + 1) * per], &tabs_src[static_cast<size_t>(u0) * per], sizeof(int32_t) * cmp_n) == 0) ++u1;
       const int32_t* t = &tabs[static_cast<size_t>(u0) * per];
       std::vector<int32_t> ud(t, t + plen[0]), uh(t + plen[0], t + plen[0] + plen[1]);
       std::sort(ud.begin(), ud.end()); ud.erase(std::unique(ud.begin(), ud.end()), ud.end());
       std::sort(uh.begin(), uh.end()); uh.erase(std::unique(uh.begin(), uh.end()), uh.end());
+      uint64_t need_w = 0;
+      if (first_win) for (int i = 0; i < plen[2]; ++i) need_w |= 1ull << (t[plen[0] + plen[1] + i] / WB);
+      else need_w = all_w;
       auto missing = [&](int32_t d) {
         Runs r;
         for (size_t i = 0; i < uh.size();) {
-          if (have[static_cast<size_t>(d) * nH + uh[i]]) { ++i; continue; }
+          const uint64_t m = need_w & ~have[static_cast<size_t>(d) * nH + uh[i]];
+          if (!m) { ++i; continue; }
           size_t j = i;
           while (j + 1 < uh.size() && uh[j + 1] == uh[j] + 1 && srcH[uh[j + 1]] == srcH[uh[j]] + 1 &&
-                 !have[static_cast<size_t>(d) * nH + uh[j + 1]]) ++j;
-          r.emplace_back(uh[i], static_cast<int32_t>(j - i + 1));
+                 (need_w & ~have[static_cast<size_t>(d) * nH + uh[j + 1]]) == m) ++j;
+          r.push_back(Run{uh[i], static_cast<int32_t>(j - i + 1), m});
           i = j + 1;
         }
         return r;
@@ -1456,38 +1477,69 @@ static int process_box_host(nbe_ctx* ctx, const void* in_host, int in_dtype, con
         const Runs r0 = missing(ud[i]);
         size_t j = i;
         while (j + 1 < ud.size() && ud[j + 1] == ud[j] + 1 && srcD[ud[j + 1]] == srcD[ud[j]] + 1 && missing(ud[j + 1]) == r0) ++j;
+        const size_t n_planes = j - i + 1;
         for (const auto& run : r0) {
-          for (int c = 0; c < 3; ++c) {
-            uint8_t* dst = static_cast<uint8_t*>(ctx->d_box) + ((static_cast<size_t>(c) * nD + ud[i]) * nH + run.first) * row_in;
-            const uint8_t* src = static_cast<const uint8_t*>(in_host) +
-                                 ((static_cast<size_t>(c) * S0 + srcD[ud[i]]) * S1 + srcH[run.first]) * row_in;
-            // own bounds check of every rectangle (compute-sanitizer is not available on this pool): last byte
-            // written / read must lie inside the device window / the caller's box
-            const size_t n_rows = j - i + 1, w_bytes = static_cast<size_t>(run.second) * row_in;
-            const size_t dst_end = static_cast<size_t>(dst - static_cast<uint8_t*>(ctx->d_box)) + (n_rows - 1) * nH * row_in + w_bytes;
-            const size_t src_end = static_cast<size_t>(src - static_cast<const uint8_t*>(in_host)) + (n_rows - 1) * S1 * row_in + w_bytes;
-            if (dst_end > in_bytes || src_end > static_cast<size_t>(3) * S0 * S1 * row_in) {
+          for (int b0 = 0; b0 < nWB;) {                     // maximal runs of missing W blocks
+            if (!((run.mask >> b0) & 1ull)) { ++b0; continue; }
+            int b1 = b0;
+            while (b1 + 1 < nWB && ((run.mask >> (b1 + 1)) & 1ull)) ++b1;
+            const int64_t wlo = b0 * WB, whi = std::min<int64_t>(S2, (b1 + 1) * WB);
+            const size_t w_bytes = static_cast<size_t>(whi - wlo) * ies;
+            // own bounds check of every box (compute-sanitizer is not available on this pool)
+            if (ud[i] + static_cast<int64_t>(n_planes) > nD || run.h0 + run.n > nH || whi > S2 ||
+                srcD[ud[i]] + static_cast<int64_t>(n_planes) > S0 || srcH[run.h0] + run.n > S1) {
               cudaStreamSynchronize(us); destroy_events();
-              return fail(ctx, NBE_ERR_STATE, "process_box upload: rectangle out of bounds (internal error)");
+              return fail(ctx, NBE_ERR_STATE, "process_box upload: box out of bounds (internal error)");
             }
-            cudaError_t e = cudaMemcpy2DAsync(dst, static_cast<size_t>(nH) * row_in, src, static_cast<size_t>(S1) * row_in,
-                                              w_bytes, n_rows, cudaMemcpyHostToDevice, us);
-            if (e != cudaSuccess) {
-              cudaStreamSynchronize(us); destroy_events();
-              return fail(ctx, NBE_ERR_CUDA, "process_box upload: %s", cudaGetErrorString(e));
+            for (int c = 0; c < 3; ++c) {
+              cudaError_t e;
+              if (w_bytes == row_in) {                      // full rows: a 2-D copy (planes x contiguous row run)
+                uint8_t* dst = static_cast<uint8_t*>(ctx->d_box) + ((static_cast<size_t>(c) * nD + ud[i]) * nH + run.h0) * row_in;
+                const uint8_t* src = static_cast<const uint8_t*>(in_host) +
+                                     ((static_cast<size_t>(c) * S0 + srcD[ud[i]]) * S1 + srcH[run.h0]) * row_in;
+                e = cudaMemcpy2DAsync(dst, static_cast<size_t>(nH) * row_in, src, static_cast<size_t>(S1) * row_in,
+                                      static_cast<size_t>(run.n) * row_in, n_planes, cudaMemcpyHostToDevice, us);
+              } else {
+                cudaMemcpy3DParms p3 = {};
+                p3.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(static_cast<const uint8_t*>(in_host)) + static_cast<size_t>(c) * S0 * S1 * row_in,
+                                                row_in, static_cast<size_t>(S2), static_cast<size_t>(S1));
+                p3.dstPtr = make_cudaPitchedPtr(static_cast<uint8_t*>(ctx->d_box) + static_cast<size_t>(c) * nD * nH * row_in,
+                                                row_in, static_cast<size_t>(S2), static_cast<size_t>(nH));
+                p3.srcPos = make_cudaPos(static_cast<size_t>(wlo) * ies, static_cast<size_t>(srcH[run.h0]), static_cast<size_t>(srcD[ud[i]]));
+                p3.dstPos = make_cudaPos(static_cast<size_t>(wlo) * ies, static_cast<size_t>(run.h0), static_cast<size_t>(ud[i]));
+                p3.extent = make_cudaExtent(w_bytes, static_cast<size_t>(run.n), n_planes);
+                p3.kind = cudaMemcpyHostToDevice;
+                e = cudaMemcpy3DAsync(&p3, us);
+              }
+              if (e != cudaSuccess) {
+                cudaStreamSynchronize(us); destroy_events();
+                return fail(ctx, NBE_ERR_CUDA, "process_box upload: %s", cudaGetErrorString(e));
+              }
             }
+            b0 = b1 + 1;
           }
           for (size_t q = i; q <= j; ++q)
-            for (int32_t h = run.first; h < run.first + run.second; ++h) have[static_cast<size_t>(ud[q]) * nH + h] = 1;
+            for (int32_t h = run.h0; h < run.h0 + run.n; ++h) have[static_cast<size_t>(ud[q]) * nH + h] |= run.mask;
           any = true;
         }
         i = j + 1;
       }
       if (any) {
-        cudaEventCreateWithFlags(&up_ev[u0], cudaEventDisableTiming);
+        if (ctx->trace) cudaEventCreate(&up_ev[u0]); else cudaEventCreateWithFlags(&up_ev[u0], cudaEventDisableTiming);
         cudaEventRecord(up_ev[u0], us);
       }
       u0 = u1 + 1;
+    }
+    if (ctx->trace) {           // NBE_TRACE=1: when did the first unit's window land, when the last one
+      cudaStreamSynchronize(us);
+      float t_first = 0.f, t_last = 0.f;
+      cudaEvent_t last = nullptr;
+      for (auto e : up_ev) if (e) last = e;
+      if (up_ev[0]) cudaEventElapsedTime(&t_first, tr0, up_ev[0]);
+      if (last) cudaEventElapsedTime(&t_last, tr0, last);
+      fprintf(stderr, "[nbe trace] gpu %d: upload window %lld x %lld rows, first unit after %.2f ms, all after %.2f ms (%.1f MB)\n",
+              ctx->device, (long long)nD, (long long)nH, t_first, t_last, in_bytes / 1e6);
+      cudaEventDestroy(tr0);
     }
   }
   cudaEvent_t done;
@@ -1705,6 +1757,21 @@ int nbe_za_psi_k(nbe_ctx* ctx, const void* delta_k_dev, int32_t res, float boxsi
       static_cast<const float2*>(delta_k_dev), res, boxsize / 6.283185307179586f, static_cast<float2*>(psi_k_dev));
   ctx->launches += 1;
   CK(cudaGetLastError());
+  return NBE_OK;
+}
+
+// Give the activation arena, the cached plans and the box staging buffers back to the driver (they are
+// re-created on demand).  Parameters and packed weights stay.
+int nbe_release_workspace(nbe_ctx* ctx) {
+  if (!ctx) return NBE_ERR_ARG;
+  ENTER_DEVICE(ctx);
+  CK(cudaDeviceSynchronize());
+  for (auto* p : ctx->plans) { if (p->dev_launches) cudaFree(p->dev_launches); delete p; }
+  ctx->plans.clear();
+  cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_cap = 0;
+  cudaFree(ctx->d_box); ctx->d_box = nullptr; ctx->box_cap = 0;
+  cudaFree(ctx->d_disp); ctx->d_disp = nullptr; ctx->out_cap = 0;
+  cudaFree(ctx->d_velo); ctx->d_velo = nullptr; ctx->velo_cap = 0;
   return NBE_OK;
 }
 

@@ -444,7 +444,10 @@ class SubboxProcessor:
             torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1)
         nbytes = recv.numel() * recv.element_size()
+        link = nbytes * (world - 1) // world       # bytes this rank receives from its peers over NVLink
         self.last_gather = {"bytes": int(nbytes), "ms": float(ms), "GBps": nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                            "nvlink_bytes_in_per_rank": int(link),
+                            "nvlink_GBps_in_per_rank": link / (ms * 1e-3) / 1e9 if ms > 0 else None,
                             "ranks_aligned": bool(self.time_gather),
                             "collective": "ncclAllGather of (subbox, 3, c0, c1, c2) records, device to device"}
         if self.compute_vel:
