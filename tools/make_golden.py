@@ -130,7 +130,7 @@ def cand(kind, seed):
     return with_cond(field((1, 3, 128, 128, 128), seed), 0.5, 0.3, seed=seed, shape=(128, 128, 128))
 
 
-ALL = dict(n224=g_n224, illcond=g_illcond, box64=g_box64, n104=g_n104, batch2=g_batch2, noncubic=g_noncubic, box=g_box, n128=g_n128)
+ALL = dict(n224=g_n224, box64=g_box64, n104=g_n104, batch2=g_batch2, noncubic=g_noncubic, box=g_box, n128=g_n128)
 for name in (sys.argv[1:] or list(ALL)):
     t = time.time()
     r = cand(*name.split('_')[1:3][:1], int(name.split('_')[2])) if name.startswith('cand_') else ALL[name]()
