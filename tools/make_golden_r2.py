@@ -6,10 +6,10 @@ heavy      N = 104 Style+vel with HEAVY-TAILED, SCALE-SPREAD weights (Student-t(
            input-channel scale x3, style_weight x2, bias x3): fp16 hi/lo split, 2^8 weight scaling and
            subnormal handling of the packed operands are exercised away from the N(0,1)/sqrt(fan_in) init
 scale01/10 N = 104 with the input field x0.1 / x10 (range check of the fp16 activations)
-n224_full  224^3 -> 128^3 (BASELINE config 3 subbox) fp64 truth of the FULL output volume, assembled from
-           2x2x2 output blocks of 64^3 computed from 160^3 input windows (VALID convs are translation-
-           consistent; a 224^3 fp64 forward does not fit this container), stored at stride 2
-n224_block one 64^3 output block (the [0:64]^3 corner) of another seed, stride 2
+n224_full  224^3 -> 128^3 (BASELINE config 3 subbox): fp64 truth of the eight 32^3 CORNER blocks of the output
+           (1/8 of the volume), each an fp64 forward of the 128^3 input window behind it (VALID convs are
+           translation-consistent; fp64 windows larger than 128^3 do not fit this container's 62 GB)
+n224_block two 32^3 blocks (a corner and the centre) of another seed
 pk256      256^3 box, ndiv 2 (eight 224^3 subboxes), fp32 oracle: P(k) of the CIC density of the displaced
            lattice (oracle/density.py) + a stride-8 subsample of disp / vel
 """
@@ -72,32 +72,30 @@ def g_scale(s):
     return with_cond(init_params(42), (field((1, 3, 104, 104, 104), 1234) * np.float32(s)), 0.5, 0.3, seed=1234, scale=s, N=104)
 
 
-def n224(seed, blocks):
+def n224_blocks(seed, offsets):
+    """fp64 truth of 32^3 output blocks of the 224^3 -> 128^3 subbox: block at output offset (a, b, c) is an fp64
+    forward of the 128^3 input window starting there (VALID convolutions are translation-consistent).  Larger fp64
+    windows do not fit this container: torch's fp64 conv3d materialises 27 x 64 columns per output voxel (52 GB
+    at 160^3)."""
     P = init_params(42)
     x = field((1, 3, 224, 224, 224), seed)
     Dz, vf = cosmo(0.5, 0.3)
-    d = np.zeros((1, 3, 128, 128, 128), np.float32); v = np.zeros_like(d)
-    for (i, j, k) in blocks:
+    ds, vs = [], []
+    for (a, b, c) in offsets:
         t = time.time()
-        xs = x[:, :, 64 * i:64 * i + 160, 64 * j:64 * j + 160, 64 * k:64 * k + 160]
-        db, vb = run(P, xs, 0.3, Dz, vf, torch.float64)
-        d[:, :, 64 * i:64 * i + 64, 64 * j:64 * j + 64, 64 * k:64 * k + 64] = db
-        v[:, :, 64 * i:64 * i + 64, 64 * j:64 * j + 64, 64 * k:64 * k + 64] = vb
-        print('  block', (i, j, k), '%.0fs' % (time.time() - t), flush=True)
-    return d, v
+        db, vb = run(P, x[:, :, a:a + 128, b:b + 128, c:c + 128], 0.3, Dz, vf, torch.float64)
+        ds.append(db[0].astype(np.float32)); vs.append(vb[0].astype(np.float32))
+        print('  block', (a, b, c), '%.0fs' % (time.time() - t), flush=True)
+    return dict(disp=np.stack(ds), vel=np.stack(vs), offsets=np.array(offsets, np.int32), seed=seed, N=224, z=0.5, Om=0.3,
+                truth='fp64 oracle, 32^3 output blocks from 128^3 input windows')
 
 
-def g_n224_full(seed):
-    blocks = [(i, j, k) for i in range(2) for j in range(2) for k in range(2)]
-    d, v = n224(seed, blocks)
-    return dict(disp=d[:, :, ::2, ::2, ::2], vel=v[:, :, ::2, ::2, ::2], seed=seed, N=224, stride=2, z=0.5, Om=0.3,
-                truth='fp64 oracle, 2x2x2 output blocks of 64^3 from 160^3 input windows')
+def g_n224_full(seed):        # the eight corner blocks: 1/8 of the output volume, spread over it
+    return n224_blocks(seed, [(a, b, c) for a in (0, 96) for b in (0, 96) for c in (0, 96)])
 
 
-def g_n224_block(seed):
-    d, v = n224(seed, [(0, 0, 0)])
-    return dict(disp=d[:, :, :64:2, :64:2, :64:2], vel=v[:, :, :64:2, :64:2, :64:2], seed=seed, N=224, stride=2, block=64,
-                z=0.5, Om=0.3, truth='fp64 oracle, output block [0:64]^3 from the [0:160]^3 input window')
+def g_n224_block(seed):       # two blocks: one corner, one centre
+    return n224_blocks(seed, [(0, 0, 0), (48, 48, 48)])
 
 
 def g_pk256():
