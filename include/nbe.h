@@ -194,6 +194,16 @@ int nbe_get_profile(nbe_ctx* ctx, int cap, const char** names, float* ms, double
  * 2 tangent) of the most recent plan.  host == NULL queries the size.                     */
 long long nbe_debug_read_act(nbe_ctx* ctx, int act, int which, void* host, size_t cap, int32_t shape_out[4]);
 
+/* Tangent folding: the reference's modulated tangent weights are
+ * dW = W (.) (a_i + beta_o) (style_layers_vel.py:86-93), so x*dW + dx*W = (dx + a (.) x)*W + beta (.) (x*W).
+ * When active (default; NBE_FOLD=0 disables, and a modulation close to zero switches it off by itself) the
+ * 64-output 3^3 launches run 4 tensor-core products per layer instead of 5 and the stored tangent of the tensors
+ * they read is dx' = dx + a (.) x.  nbe_fold_active reports the state after the last nbe_modulate;
+ * nbe_debug_act_fold copies the fold vector a of activation `act` (zeros if it has none) and returns its
+ * channel count.                                                                           */
+int nbe_fold_active(nbe_ctx* ctx);
+int nbe_debug_act_fold(nbe_ctx* ctx, int act, int sample, float* a_host, int cap);
+
 #ifdef __cplusplus
 }
 #endif

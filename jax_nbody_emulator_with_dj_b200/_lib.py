@@ -25,6 +25,7 @@ EXPORTS = (
     "nbe_process_box_multi", "nbe_process_box_blocks",
     "nbe_workspace_bytes", "nbe_release_workspace", "nbe_host_register", "nbe_host_unregister",
     "nbe_launch_count", "nbe_set_profiling", "nbe_get_profile", "nbe_debug_read_act",
+    "nbe_fold_active", "nbe_debug_act_fold",
     "nbe_density_from_psi", "nbe_mas_deconvolve", "nbe_pk_bins", "nbe_za_psi_k",
 )
 
@@ -106,6 +107,8 @@ def load():
         lib.nbe_get_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), f32p, C.POINTER(C.c_double)]
         lib.nbe_debug_read_act.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t, i32p]
         lib.nbe_debug_read_act.restype = C.c_longlong
+        lib.nbe_fold_active.argtypes = [vp]
+        lib.nbe_debug_act_fold.argtypes = [vp, C.c_int, C.c_int, f32p, C.c_int]
         for name in EXPORTS:
             getattr(lib, name)
         _lib = lib

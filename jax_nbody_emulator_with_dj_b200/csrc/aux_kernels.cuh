@@ -59,7 +59,47 @@ struct LayerMeta {
   // accumulation chains (conv_mma.cuh, EARLY == 3): kd_mask of a rule selects by the PHASE of the 3-tap
   // block a tap belongs to, phase = (chain_par0 + kd * chain_nkc + kc + kw) & 1
   int chain, chain_par0, chain_nkc;
+  // Tangent folding (conv_mma.cuh, ConvLaunch::beta / anext).  With m_i the modulation of input channel i,
+  //   dWn[o,i,t] = Wn[o,i,t] * (a_i + beta_o),   a_i = SW[i,1] / m_i,   beta_o = n_o * dn_o = -sum(w*dws) / n_o^2.
+  // The tangent rows this layer EMITS are  dWn - (f_i + bl_o) * Wn,  where f is the fold vector already added
+  // to the stored tangent of the tensor it reads (the a of that tensor's fold consumer; zero if none) and bl
+  // the beta the owning launch applies in its epilogue (the beta of the launch's main conv; zero for launches
+  // that are not FOLD instances).  For the main conv of a FOLD launch that is identically zero: no tangent rows.
+  const float* fold_SW;     // style params of the layer that defines f of this layer's source tensor (or nullptr)
+  const float* fold_sb;
+  const float* fold_a;      // premodulated weights: f itself (device, [cin]) or nullptr
+  int beta_layer;           // meta index of the layer whose beta the owning launch applies (-1: none)
+  const float* pre_a;       // premodulated weights: this layer's own a (cin) / beta (cout) from the host factorisation
+  const float* pre_beta;
+  float* beta_out;          // main conv of a FOLD launch: beta goes here ([sample][fold_stride])
+  float* a_out;             // ... and a here (the anext of the launch producing its source tensor)
+  int fold_stride;          // floats between samples in beta_out / a_out
 };
+
+// sum over (i, t) of w^2 and w * dws for output row o of layer M: every thread returns the block-wide sums
+__device__ __forceinline__ void modulate_row_sums(const LayerMeta& M, int o, float s0, float s1, float* red1,
+                                                  float* red2, float& a1, float& a2) {
+  const int ne = M.cin * M.k3;
+  const float* Wrow = M.W + static_cast<long long>(o) * ne;
+  a1 = 0.f; a2 = 0.f;
+  for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+    const int i = e / M.k3;
+    const float m = s0 * M.SW[2 * i] + s1 * M.SW[2 * i + 1] + M.sb[i];
+    const float w = Wrow[e] * m;
+    const float dws = Wrow[e] * M.SW[2 * i + 1];
+    a1 += w * w;
+    a2 += w * dws;
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+  }
+  __syncthreads();          // red1 / red2 may still be read from a previous call
+  if ((threadIdx.x & 31) == 0) { red1[threadIdx.x >> 5] = a1; red2[threadIdx.x >> 5] = a2; }
+  __syncthreads();
+  a1 = red1[0] + red1[1] + red1[2] + red1[3];
+  a2 = red2[0] + red2[1] + red2[2] + red2[3];
+}
 
 __global__ void __launch_bounds__(128)
 modulate_kernel(const LayerMeta* __restrict__ metas, int n_layers, const float* __restrict__ s0a,
@@ -80,28 +120,34 @@ modulate_kernel(const LayerMeta* __restrict__ metas, int n_layers, const float* 
   const float* Wrow = M.W + static_cast<long long>(o) * ne;
 
   float inv_n = 1.f, dn = 0.f;
+  float beta_own = 0.f;       // this layer's own beta_o
   if (!M.premod) {
-    float a1 = 0.f, a2 = 0.f;
-    for (int e = threadIdx.x; e < ne; e += blockDim.x) {
-      const int i = e / M.k3;
-      const float m = s0 * M.SW[2 * i] + s1 * M.SW[2 * i + 1] + M.sb[i];
-      const float w = Wrow[e] * m;
-      const float dws = Wrow[e] * M.SW[2 * i + 1];
-      a1 += w * w;
-      a2 += w * dws;
-    }
-    for (int off = 16; off > 0; off >>= 1) {
-      a1 += __shfl_xor_sync(0xffffffffu, a1, off);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, off);
-    }
-    if ((threadIdx.x & 31) == 0) { red1[threadIdx.x >> 5] = a1; red2[threadIdx.x >> 5] = a2; }
-    __syncthreads();
-    a1 = red1[0] + red1[1] + red1[2] + red1[3];
-    a2 = red2[0] + red2[1] + red2[2] + red2[3];
+    float a1, a2;
+    modulate_row_sums(M, o, s0, s1, red1, red2, a1, a2);
     const float n = sqrtf(a1 + eps);
     inv_n = 1.f / n;
     dn = -a2 / (n * n * n);
+    beta_own = -a2 / (a1 + eps);
+  } else if (M.pre_beta != nullptr) {
+    beta_own = M.pre_beta[o];
   }
+  // beta applied by the owning launch's epilogue (row o of its main conv)
+  float bl = 0.f;
+  if (M.vel && M.beta_layer >= 0) {
+    const LayerMeta& MB = metas[M.beta_layer];
+    if (!M.premod) {
+      float a1, a2;
+      modulate_row_sums(MB, o, s0, s1, red1, red2, a1, a2);
+      bl = -a2 / (a1 + eps);
+    } else {
+      bl = MB.pre_beta[o];
+    }
+  }
+  if (M.vel && M.beta_out != nullptr && threadIdx.x == 0) M.beta_out[static_cast<long long>(b) * M.fold_stride + o] = beta_own;
+  if (M.vel && M.a_out != nullptr && o == 0)
+    for (int i = threadIdx.x; i < M.cin; i += blockDim.x)
+      M.a_out[static_cast<long long>(b) * M.fold_stride + i] =
+          M.premod ? M.pre_a[i] : M.SW[2 * i + 1] / (s0 * M.SW[2 * i] + s1 * M.SW[2 * i + 1] + M.sb[i]);
   const float inv_Dz = 1.f / (s1 + 1.f);
   const long long sample_off = static_cast<long long>(b) * M.dst_sample_stride;
   const int rowlen = M.kc16 ? 16 : 64;
@@ -128,6 +174,12 @@ modulate_kernel(const LayerMeta* __restrict__ metas, int n_layers, const float* 
     const long long oidx = static_cast<long long>(b) * M.cout * ne + static_cast<long long>(o) * ne + e;
     M.w32[oidx] = wn;
     if (M.dw32) M.dw32[oidx] = dwn;
+    if (M.vel) {              // what the stored tangent of the source / the launch's epilogue already carry
+      float f = bl;
+      if (M.fold_SW != nullptr) f += M.fold_SW[2 * i + 1] / (s0 * M.fold_SW[2 * i] + s1 * M.fold_SW[2 * i + 1] + M.fold_sb[i]);
+      else if (M.fold_a != nullptr) f += M.fold_a[i];
+      dwn = fmaf(-f, wn, dwn);
+    }
     // operands are packed scaled by kWeightScale (a power of two, undone exactly in the conv
     // epilogue) so that lo = W - hi(W) ~ 2^-12 |W| stays a NORMAL fp16 number: unscaled, the lo
     // part of a typical demodulated weight (~0.02) is subnormal and keeps only ~5 bits.

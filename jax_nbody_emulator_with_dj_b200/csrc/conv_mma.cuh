@@ -89,6 +89,13 @@ struct alignas(128) ConvLaunch {
   __half* out_l_ptr;        // primal lo or nullptr
   __half* out_d_ptr;        // tangent or nullptr
   const float* bias;        // [cout]
+  // Tangent folding.  dW = W (.) (a_i + beta_o) for a style-modulated layer, so
+  //   x * dW + dx * W  =  (dx + a (.) x) * W  +  beta (.) (x * W):
+  // `anext` (or nullptr) is the fold vector a of the layer that consumes this launch's output -- the epilogue
+  // stores dx' = dy + anext (.) y instead of dy; `beta` (FOLD instance only) is this launch's own per-output
+  // factor, applied to the primal sum.
+  const float* beta;        // [cout] or nullptr
+  const float* anext;       // [cout] or nullptr
   int32_t cout;             // output channels (primal)
   int32_t vel;              // accumulator holds [y | dy]
   int32_t act;              // LeakyReLU
@@ -199,6 +206,12 @@ constexpr bool kBaseOffsetMode = NBE_BASE_OFFSET != 0;
 // register sum with round-to-nearest adds, re-zeroes them and arrives on y?_empty, which the issuers
 // wait on before the next chain into the same accumulator -- one whole block later.  dy and ylo
 // accumulate through the item as before.
+//
+// EARLY == 4 ("FOLD", chains + folded tangent): the consumer-side product x * dW is gone (see ConvLaunch::beta /
+// anext), so a tap is  xh * [Wl | Wh] -> (ylo, y0)  or  xh * [Wh | Wl] -> (y1, ylo)  (ONE instruction, N = 128) and
+// dx' * Wh -> dy (N = 64): 4 MMA column-blocks per k-step instead of 5.  Columns [dy | y1 | ylo | y0], 2 x 96
+// weight rows per stage.  A folded 1^3 skip conv reads a tensor with a different fold vector: its residual
+// x * dW_res -> dy is a one-tap group of its own with a short weight stage.
 template <int NRS, int DC, int TM, bool FINAL, bool PAIR = false, int EARLY = 0>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupTable gt,
@@ -224,7 +237,12 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y1_empty + 1);
   static_assert(EARLY == 0 || (Cfg::kNBuf == 1 && !FINAL && TM * DC == 512), "EARLY: single-stage acc3 instances only");
   static_assert(EARLY < 2 || (PAIR && TM == 2 && DC == 256), "F192: 64-output pair instance only");
+  constexpr bool kChain = EARLY >= 3;      // accumulation chains
+  constexpr bool kFold = EARLY == 4;       // ... with the folded tangent and the [dy | y1 | ylo | y0] layout
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);   // up to 128 floats
+  float* beta_s = bias_s + 128;
+  float* anext_s = beta_s + 128;
+  static_assert(8 * (2 * Cfg::kNAB + 2 * Cfg::kNB + 8) + 8 + 3 * 512 <= Cfg::kCtrl, "control block overflow");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -258,6 +276,12 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
   if (warp == 3) {
     const int nb = FINAL ? 16 : L->cout;
     for (int i = lane; i < nb; i += 32) bias_s[i] = L->bias[i];
+    const float* bp = L->beta;
+    const float* ap = L->anext;
+    for (int i = lane; i < 128; i += 32) {
+      beta_s[i] = (bp != nullptr && i < nb) ? bp[i] : 0.f;
+      anext_s[i] = (ap != nullptr && i < nb) ? ap[i] : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -406,7 +430,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     constexpr uint32_t idesc_base = umma_idesc_f16(PAIR ? 256 : 128, 0, false);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0, buf = 0, pacc = 0;
-    uint32_t pe = 0;      // EARLY == 3: bit a = parity of the next wait on y<a>_empty
+    uint32_t pe = 0;      // chains: bit a = parity of the next wait on y<a>_empty
     for (long long item = item_first; item < n_items && (!PAIR || rank == 0); item += gridDim.x) {
       if constexpr (EARLY == 0) {
         mbar_wait(&acc_empty[buf], pacc ^ 1);
@@ -420,7 +444,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
           // pre_wait 1: y0_empty, 2: acc_empty, 3: y1_empty.  All are signalled by the PREVIOUS item's
           // epilogue, except y0_empty in the F192 layout, which kd 2 needs from the CURRENT item
           const int pw = G.pre_wait;
-          if (EARLY == 3 && pw == 3) {            // start of the lo chain (into y1)
+          if (kChain && pw == 3) {                // start of the lo chain (into y1)
             mbar_wait(y1_empty, ((pe >> 1) & 1u) ^ 1u);
             pe ^= 2u;
             tc_fence_after();
@@ -500,7 +524,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
           // accumulator must have been drained since its previous chain
           uint32_t chain_p = 0u, d_sel = op_d[0];
           bool chain_end = false;
-          if constexpr (EARLY == 3) {
+          if constexpr (kChain) {
             if (G.chain != 0) {
               chain_p = (static_cast<uint32_t>(G.phase0) + static_cast<uint32_t>(j) / 3u) & 1u;
               if (j % 3 == 0) {
@@ -508,7 +532,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
                 pe ^= (1u << chain_p);
                 tc_fence_after();
               }
-              d_sel = chain_p ? 0u : op_d[0];
+              d_sel = chain_p ? (kFold ? static_cast<uint32_t>(DC / 4) : 0u) : op_d[0];
               chain_end = (j % 3 == 2) || (j == ntaps - 1);
             }
           }
@@ -550,7 +574,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
               }
             }
             if (jt == tps - 1) commit(&b_empty[sb]);
-            if constexpr (EARLY == 3) {
+            if constexpr (kChain) {
               if (chain_end) commit(chain_p ? y1_full : y0_full);
             }
           }
@@ -591,6 +615,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
     const bool vel = L->vel != 0;
     const bool act = L->act != 0;
     const bool acc3 = L->acc3 != 0;
+    const bool fold_out = L->anext != nullptr;
     const int64_t out_sw = L->out_sw, out_sh = L->out_sh, out_sd = L->out_sd;
     const int64_t par_ow = L->par_ow, par_oh = L->par_oh, par_od = L->par_od;
     __half* const out_h_ptr = L->out_h_ptr;
@@ -603,12 +628,12 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
       // take alternate chunks of the 128)
       constexpr int COUT = DC / 4;
       constexpr int cY0 = EARLY >= 2 ? 3 * COUT : 0;          // first primal accumulator to complete
-      constexpr int cY1 = EARLY >= 2 ? 0 : 2 * COUT;          // second
-      uint32_t pf = 0;                                        // EARLY == 3: bit a = parity of the next wait on y<a>_full
+      constexpr int cY1 = kFold ? COUT : (EARLY >= 2 ? 0 : 2 * COUT);   // second
+      uint32_t pf = 0;                                        // chains: bit a = parity of the next wait on y<a>_full
       const int n_chains = L->n_chains;
       constexpr int cYZ = 3 * COUT;                           // last: y2, or y0 re-used by kd 2
-      constexpr int cDY = COUT;
-      constexpr int cLO = 2 * COUT;                           // F192 only: xh * Wl
+      constexpr int cDY = kFold ? 0 : COUT;
+      constexpr int cLO = 2 * COUT;                           // F192 / FOLD only: xh * Wl
       const int t = TM == 2 ? eg : 0;
       auto ch = [&](int i) { return TM == 1 ? eg * 32 + 64 * i : 32 * i; };
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * DC;
@@ -625,7 +650,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
         const int h = h0 + t * 16 + (r >> 3);
         const bool valid = item_ok && (w < out_w) && (h < out_h);
         uint32_t ps[64];
-        if constexpr (EARLY == 3) {
+        if constexpr (kChain) {
           // accumulation chains: chain 0 (lo phase) comes back in y1, chain c >= 1 in y0 / y1 alternately
 #pragma unroll
           for (int k = 0; k < 64; ++k) ps[k] = 0u;
@@ -701,11 +726,11 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
             for (int hf = 0; hf < 2; ++hf) {
               const int c = ch(i) + 16 * hf;
               uint32_t y2[16], dy[16], yl[16];
-              if constexpr (EARLY != 3) tmem_ld16(taddr + cYZ + c, y2);
+              if constexpr (!kChain) tmem_ld16(taddr + cYZ + c, y2);
               tmem_ld16(taddr + cDY + c, dy);
               if constexpr (EARLY >= 2) tmem_ld16(taddr + cLO + c, yl);
               tmem_ld_wait();
-              if constexpr (EARLY != 3) tmem_st16_zero(taddr + cYZ + c);
+              if constexpr (!kChain) tmem_st16_zero(taddr + cYZ + c);
               tmem_st16_zero(taddr + cDY + c);
               if constexpr (EARLY >= 2) tmem_st16_zero(taddr + cLO + c);
               uint32_t ph[8], pl[8], pd[8];
@@ -713,7 +738,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
               for (int j = 0; j < 16; j += 2) {
                 float s0 = __uint_as_float(ps[32 * i + 16 * hf + j]);
                 float s1 = __uint_as_float(ps[32 * i + 16 * hf + j + 1]);
-                if constexpr (EARLY != 3) {
+                if constexpr (!kChain) {
                   s0 += __uint_as_float(y2[j]);
                   s1 += __uint_as_float(y2[j + 1]);
                 }
@@ -725,12 +750,19 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
                 float y1v = s1 * kInvWeightScale + bias_s[c + j + 1];
                 float d0v = __uint_as_float(dy[j]) * kInvWeightScale;
                 float d1v = __uint_as_float(dy[j + 1]) * kInvWeightScale;
+                if constexpr (kFold) {      // + beta_o * (x * W)_o: the demodulation part of x * dW
+                  d0v = fmaf(beta_s[c + j], s0 * kInvWeightScale, d0v);
+                  d1v = fmaf(beta_s[c + j + 1], s1 * kInvWeightScale, d1v);
+                }
                 if (act) {
                   d0v = y0v > 0.f ? d0v : 0.01f * d0v;
                   d1v = y1v > 0.f ? d1v : 0.01f * d1v;
                   y0v = y0v >= 0.f ? y0v : 0.01f * y0v;
                   y1v = y1v >= 0.f ? y1v : 0.01f * y1v;
                 }
+                // the consumer's fold vector: it multiplies dx' = dy + a (.) y by W (anext_s is zero without one)
+                d0v = fmaf(anext_s[c + j], y0v, d0v);
+                d1v = fmaf(anext_s[c + j + 1], y1v, d1v);
                 const __half2 hh = __floats2half2_rn(y0v, y1v);
                 const float2 hf2 = __half22float2(hh);
                 const __half2 ll = __floats2half2_rn(y0v - hf2.x, y1v - hf2.y);
@@ -835,6 +867,10 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
                 d1v = y1 > 0.f ? d1v : 0.01f * d1v;
                 y0 = y0 >= 0.f ? y0 : 0.01f * y0;
                 y1 = y1 >= 0.f ? y1 : 0.01f * y1;
+              }
+              if (fold_out) {                               // the consumer's fold vector
+                d0v = fmaf(anext_s[c + i], y0, d0v);
+                d1v = fmaf(anext_s[c + i + 1], y1, d1v);
               }
               const __half2 hh = __floats2half2_rn(y0, y1);
               const float2 hf = __half22float2(hh);

@@ -31,8 +31,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 enum ConvType { T_CONV3 = 0, T_SKIP1 = 1, T_DOWN = 2, T_UP = 3 };
-enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_PAIR_256_512_1, I_PAIR_128_128_2, I_PAIR_256_256_1, I_PAIR_128_256_1, I_EARLY_128_256_2, I_EARLY_256_512_1, I_F192_2, I_CHAIN_2, I_COUNT };
-struct InstInfo { int nrs, dc, tm; bool fin; bool pair = false; bool acc3 = false; bool early = false; bool f192 = false; bool chain = false; };
+enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_PAIR_256_512_1, I_PAIR_128_128_2, I_PAIR_256_256_1, I_PAIR_128_256_1, I_EARLY_128_256_2, I_EARLY_256_512_1, I_F192_2, I_CHAIN_2, I_FOLD_2, I_COUNT };
+struct InstInfo { int nrs, dc, tm; bool fin; bool pair = false; bool acc3 = false; bool early = false; bool f192 = false; bool chain = false; bool fold = false; };
 const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32, 16, 2, true},
                                  {128, 64, 2, false},  {64, 64, 2, false},   {256, 128, 1, false},
                                  {128, 256, 2, false, false, true}, {256, 512, 1, false, false, true},
@@ -46,7 +46,9 @@ const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32
                                  // F192: N = 192 fused [Wh|dW|Wl] main product, 2 x 128 weight rows per stage (conv_mma.cuh, EARLY == 2)
                                  {256, 256, 2, false, true, true, true, true},
                                  // F192 + accumulation chains (EARLY == 3): the two primal accumulators alternate every 3 taps
-                                 {256, 256, 2, false, true, true, true, true, true}};
+                                 {256, 256, 2, false, true, true, true, true, true},
+                                 // FOLD (EARLY == 4): chains + folded tangent, N = 128 main product, 2 x 96 weight rows per stage
+                                 {192, 256, 2, false, true, true, true, true, true, true}};
 
 // activation tensors of the net
 enum ActId {
@@ -55,7 +57,11 @@ enum ActId {
 };
 
 struct Src { int act; int crop; int c0; bool kc16; };
-struct ConvPart { int layer; int type; int off; std::vector<Src> src; int tile_base64 = 0, tile_base16 = 0; };
+struct ConvPart {
+  int layer; int type; int off; std::vector<Src> src; int tile_base64 = 0, tile_base16 = 0;
+  int fold_layer = -1;      // layer whose fold vector a is already in the stored tangent of this part's source tensor
+  int beta_layer = -1;      // layer whose beta the owning launch's epilogue applies (-1: none, or this part itself)
+};
 struct StaticLaunch {
   std::string name;
   int inst;
@@ -67,6 +73,9 @@ struct StaticLaunch {
   long long b64_off = 0, b16_off = 0;
   int n_tiles64 = 0, n_tiles16 = 0;
   long long bias_off = 0;   // floats, in the bias buffer
+  // tangent folding (conv_mma.cuh, ConvLaunch::beta / anext)
+  int beta_layer = -1;      // FOLD instance: layer whose beta the epilogue applies (the launch's 3^3 conv)
+  int anext_layer = -1;     // layer whose fold vector a the epilogue adds to the stored tangent (fold consumer of out_act)
 };
 
 struct ActBuf { int c = 0, d = 0, h = 0, w = 0; size_t off_hi = 0, off_lo = 0, off_dx = 0; };
@@ -96,6 +105,10 @@ struct Layer {
   float *W = nullptr, *dW = nullptr, *SW = nullptr, *sb = nullptr;   // device
   std::vector<float> bias;
   long long w32_off = 0;    // floats into w32 / dw32 per sample
+  std::vector<float> hSW, hsb;              // host copies of the style parameters (fold range check)
+  float *pre_a = nullptr, *pre_beta = nullptr;   // premodulated weights: dW = W (.) (a_i + beta_o) factorisation (device)
+  std::vector<float> h_pre_a;
+  bool pre_ok = false;
 };
 
 }  // namespace
@@ -120,6 +133,10 @@ struct nbe_ctx {
   bool trace = false;       // NBE_TRACE=1: upload timings on stderr (synchronises the upload stream: not for benchmarks)
   bool w_window = true;     // the first subbox's upload is windowed in W as well (NBE_WWIN=0: whole rows)
   bool chain = true;        // ... with accumulation chains of 3 taps (NBE_CHAIN=0: one chain per kd-plane)
+  bool fold = true;         // ... and the folded tangent (4 instead of 5 products; NBE_FOLD=0 disables)
+  bool fold_active = false; // what build_static used: fold && every fold vector in range (checked per modulation)
+  float fold_amax = 64.f;   // |a_i| above this (a modulation m_i close to zero) switches folding off (NBE_FOLD_AMAX)
+  float* d_fold = nullptr; size_t fold_cap = 0;      // [sample][launch][beta 128 | anext 128] floats
   int band_h = 2;           // tile rows per h-band of the item order (NBE_BAND; 0: whole planes)
   bool wide16 = true;       // also for the 16-channel first layer (32-byte rows, SWIZZLE_32B row shifts; NBE_WIDE16)
   bool wide = true;         // w-halo'd activation blocks serving 9 taps per load (NBE_WIDE=0 disables)
@@ -213,6 +230,70 @@ int find_layer(nbe_ctx* ctx, const char* block, const char* layer) {
 }
 
 // ----------------------------------------------------------------------------------------
+// tangent folding: which layers can be the 3^3 conv of a FOLD launch, and whether their fold vectors are usable
+// ----------------------------------------------------------------------------------------
+bool fold_candidate(const Layer& l) { return l.k == 3 && l.cout == 64 && l.cin >= 64; }
+
+// Premodulated weights arrive as (W, dW) without the style parameters.  The reference's modulation gives
+// dW[o,i,t] = W[o,i,t] * (a_i + beta_o) (style_layers_vel.py:86-93): recover a and beta from the per-(o,i) ratio
+// R = <dW, W>_t / <W, W>_t = a_i + beta_o  (column means, row means minus the overall mean) and verify the
+// structure element by element.  A tree that does not have it (hand-made dweight) keeps the 5-product kernels.
+void factor_premod(Layer& L, const float* W, const float* dW, float amax, std::vector<float>& a, std::vector<float>& beta) {
+  const int O = L.cout, I = L.cin, T = L.k * L.k * L.k;
+  std::vector<double> R(static_cast<size_t>(O) * I);
+  L.pre_ok = false;
+  double dmax = 0;
+  for (int o = 0; o < O; ++o)
+    for (int i = 0; i < I; ++i) {
+      double num = 0, den = 0;
+      const size_t base = (static_cast<size_t>(o) * I + i) * T;
+      for (int t = 0; t < T; ++t) { num += static_cast<double>(dW[base + t]) * W[base + t]; den += static_cast<double>(W[base + t]) * W[base + t];
+                                    dmax = std::max(dmax, std::fabs(static_cast<double>(dW[base + t]))); }
+      if (!(den > 0)) return;
+      R[static_cast<size_t>(o) * I + i] = num / den;
+    }
+  std::vector<double> col(I, 0.0), row(O, 0.0);
+  double mean = 0;
+  for (int o = 0; o < O; ++o) for (int i = 0; i < I; ++i) { const double r = R[static_cast<size_t>(o) * I + i]; col[i] += r / O; row[o] += r / I; mean += r / (static_cast<double>(O) * I); }
+  a.resize(I); beta.resize(O);
+  for (int i = 0; i < I; ++i) { a[i] = static_cast<float>(col[i]); if (!(std::fabs(col[i]) <= amax)) return; }
+  for (int o = 0; o < O; ++o) beta[o] = static_cast<float>(row[o] - mean);
+  double worst = 0;
+  for (int o = 0; o < O; ++o)
+    for (int i = 0; i < I; ++i) {
+      const size_t base = (static_cast<size_t>(o) * I + i) * T;
+      const double f = static_cast<double>(a[i]) + beta[o];
+      for (int t = 0; t < T; ++t) worst = std::max(worst, std::fabs(dW[base + t] - f * W[base + t]));
+    }
+  L.pre_ok = worst <= 1e-4 * dmax;
+}
+
+bool fold_static_ok(const nbe_ctx* ctx) {
+  if (!ctx->fold || !ctx->vel || ctx->precision != NBE_PREC_SPLIT || !ctx->pair || !ctx->wide || !ctx->f192 ||
+      !ctx->chain || ctx->dbuf)
+    return false;
+  if (ctx->premod)
+    for (const auto& l : ctx->layers)
+      if (fold_candidate(l) && !l.pre_ok) return false;
+  return true;
+}
+
+// style models: every fold vector a_i = SW[i,1] / m_i of every candidate layer must be moderate for all samples
+bool fold_range_ok(const nbe_ctx* ctx, const std::vector<float>& s0, const std::vector<float>& s1) {
+  if (ctx->premod) return true;
+  for (const auto& l : ctx->layers) {
+    if (!fold_candidate(l)) continue;
+    for (size_t b = 0; b < s0.size(); ++b)
+      for (int i = 0; i < l.cin; ++i) {
+        const float m = s0[b] * l.hSW[2 * i] + s1[b] * l.hSW[2 * i + 1] + l.hsb[i];
+        const float a = l.hSW[2 * i + 1] / m;
+        if (!(std::fabs(a) <= ctx->fold_amax)) return false;
+      }
+  }
+  return true;
+}
+
+// ----------------------------------------------------------------------------------------
 // static description of the net as fused launches (see DESIGN.md "launch list")
 // ----------------------------------------------------------------------------------------
 int build_static(nbe_ctx* ctx) {
@@ -276,11 +357,41 @@ int build_static(nbe_ctx* ctx) {
       if (!ok) continue;
       if (s.inst == I_128_256_2)
         s.inst = ctx->dbuf ? I_PAIR_128_256_1
-                 : (ctx->f192 ? (ctx->chain ? I_CHAIN_2 : I_F192_2) : (ctx->early ? I_EARLY_128_256_2 : I_PAIR_128_256_2));
+                 : (ctx->f192 ? (ctx->chain ? (ctx->fold_active ? I_FOLD_2 : I_CHAIN_2) : I_F192_2)
+                              : (ctx->early ? I_EARLY_128_256_2 : I_PAIR_128_256_2));
       else if (s.inst == I_256_512_1) s.inst = ctx->early ? I_EARLY_256_512_1 : I_PAIR_256_512_1;
       else if (s.inst == I_128_128_2) s.inst = I_PAIR_128_128_2;
       else if (s.inst == I_256_256_1) s.inst = I_PAIR_256_256_1;
     }
+
+  // ---- tangent folding: the 3^3 conv of a FOLD launch defines the fold vector of the tensor(s) it reads; the
+  // launch producing such a tensor adds a (.) y to the tangent it stores, every other reader subtracts it again
+  // in its tangent weights (modulate_kernel)
+  {
+    std::vector<int> act_fold(A_COUNT, -1);
+    for (auto& s : ctx->sl) {
+      if (!kInst[s.inst].fold) continue;
+      for (auto& p : s.parts)
+        if (p.type == T_CONV3) {
+          s.beta_layer = p.layer;
+          for (auto& sc : p.src) {
+            if (act_fold[sc.act] >= 0 && act_fold[sc.act] != p.layer)
+              return fail(ctx, NBE_ERR_STATE, "launch %s: source tensor already has a fold consumer", s.name.c_str());
+            act_fold[sc.act] = p.layer;
+          }
+        }
+    }
+    for (auto& s : ctx->sl) {
+      s.anext_layer = (vel && s.out_act >= 0 && s.out_act < A_COUNT) ? act_fold[s.out_act] : -1;
+      for (auto& p : s.parts) {
+        p.fold_layer = act_fold[p.src[0].act];
+        for (auto& sc : p.src)
+          if (act_fold[sc.act] != p.fold_layer)
+            return fail(ctx, NBE_ERR_STATE, "launch %s: sources with different fold vectors", s.name.c_str());
+        p.beta_layer = (s.beta_layer >= 0 && s.beta_layer != p.layer) ? s.beta_layer : -1;
+      }
+    }
+  }
 
   // ---- weight layout: tiles, emit rules, LayerMeta
   const int nkind = (vel && split) ? 2 : 1;
@@ -298,7 +409,8 @@ int build_static(nbe_ctx* ctx) {
       const Layer& ly = ctx->layers[p.layer];
       const bool k16 = p.src[0].kc16;
       const int nkc = static_cast<int>(p.src.size());
-      const int nk = k16 ? 1 : nkind;
+      // FOLD: the folded 1^3 skip has a third tile kind, its residual tangent rows (x * dW_res -> dy)
+      const int nk = k16 ? 1 : ((ii.fold && p.type == T_SKIP1) ? 3 : nkind);
       LayerMeta& M = ctx->metas[p.layer];
       int& tb = k16 ? t16 : t64;
       (k16 ? p.tile_base16 : p.tile_base64) = tb;
@@ -345,6 +457,25 @@ int build_static(nbe_ctx* ctx) {
           rule(EMIT_WH, 0, 0, 0);
           if (split) { rule(EMIT_WL, 0, 8, 0); rule(EMIT_WH, 0, 16, 0); }
         }
+      } else if (ii.fold && k16) {   // 16-channel folded skip of a FOLD launch: N = 2C rows [dW | Wh..] -> (dy, y1)
+        prule(EMIT_DW, 0, 0, 0, C, 0, 0);
+        prule(EMIT_WH, 0, 0, 1, C, 0, 0); prule(EMIT_WH, 0, 0, 1, C, 0, 3); prule(EMIT_WL, 0, 0, 1, C, 0, 6);
+      } else if (ii.fold) {
+        // per-CTA stage (1.5C rows): rows [0, C) = this CTA's half of the N = 2C operand ([Wl | Wh] -> (ylo, y0) for
+        // blocks of phase 0, [Wh | Wl] -> (y1, ylo) for phase 1), rows [C, 1.5C) = its half of Wh for dx' * Wh.
+        // lo stage: this CTA's half of Wh (xl * Wh -> y1); skip only: its half of the residual tangent rows.
+        auto xrule = [&](int what, int kind, int kdmask, int cta, int base, int o0, int o1) {
+          EmitRule& R = M.rules[nr++];
+          R.what = static_cast<int8_t>(what); R.kind = static_cast<int8_t>(kind); R.row_base = static_cast<int16_t>(base);
+          R.kcol = 0; R.alt_kd1 = 0; R.mod = 0; R.cta_base = static_cast<int8_t>(cta); R.kd_mask = static_cast<int8_t>(kdmask);
+          R.o_min = static_cast<int16_t>(o0); R.o_max = static_cast<int16_t>(o1);
+        };
+        const int H2 = C / 2;
+        xrule(EMIT_WL, 0, 0b01, 0, 0, 0, C);         xrule(EMIT_WH, 0, 0b01, 1, 0, 0, C);
+        xrule(EMIT_WH, 0, 0b10, 0, 0, 0, C);         xrule(EMIT_WL, 0, 0b10, 1, 0, 0, C);
+        xrule(EMIT_WH, 0, 0, 0, C, 0, H2);           xrule(EMIT_WH, 0, 0, 1, C, H2, C);           // dx' * Wh halves
+        xrule(EMIT_WH, 1, 0, 0, 0, 0, H2);           xrule(EMIT_WH, 1, 0, 1, 0, H2, C);           // lo stage
+        if (p.type == T_SKIP1) { xrule(EMIT_DW, 2, 0, 0, 0, 0, H2); xrule(EMIT_DW, 2, 0, 1, 0, H2, C); }
       } else if (ii.pair && k16) {   // N = 2C rows [Wh.. | dW]: CTA0 stages the primal rows, CTA1 the tangent rows
         prule(EMIT_WH, 0, 0, 0, C, 0, 0); prule(EMIT_WH, 0, 0, 0, C, 0, 3); prule(EMIT_WL, 0, 0, 0, C, 0, 6);
         prule(EMIT_DW, 0, 0, 1, C, 0, 0);
@@ -612,10 +743,11 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
       // main groups are further ordered by the accumulator they complete: kd 0 and the folded skip
       // (y0, dy) | kd 1 (dy, y1) | kd 2 (y2, dy), which is what lets the EARLY instances drain y0 / y1
       // while later kd-planes are still running
-      std::vector<GroupDesc> g_lo, g_main[3], g_skip16, g_skip64;   // the skip lists are used by the chain instance only
+      std::vector<GroupDesc> g_lo, g_main[3], g_skip16, g_skip64, g_dwres;   // the skip lists are used by the chain instances only
       int cur_kind = 0, cur_kd = 0, cur_skip = 0;
       auto push = [&](const GroupDesc& G) {
         if (cur_kind == 1) g_lo.push_back(G);
+        else if (cur_kind == 2) g_dwres.push_back(G);
         else if (ii.chain && cur_skip == 1) g_skip16.push_back(G);
         else if (ii.chain && cur_skip == 2) g_skip64.push_back(G);
         else g_main[cur_kd].push_back(G);
@@ -628,7 +760,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
         const Layer& ly = ctx->layers[p.layer];
         const int nkc = static_cast<int>(p.src.size());
         const bool k16 = p.src[0].kc16;
-        const int nk = k16 ? 1 : nkind;
+        const int nk = k16 ? 1 : ((ii.fold && p.type == T_SKIP1) ? 3 : nkind);
         const int C = ly.cout;
         const int tb = k16 ? p.tile_base16 : p.tile_base64;
         // OP(a, n8, b_row, d_col) -> device layout with byte offsets >> 4 precomputed
@@ -645,9 +777,17 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           const bool acc3 = ii.acc3 && !k16;
           const __half* ph = hi(sc.act);
           if (ii.f192 && !k16) {
-            if (kind == 1) {      // lo phase: xl * Wh -> y1 (column 0)
+            if (kind == 1) {      // lo phase: xl * Wh -> y1 (column 0; FOLD layout: column C)
               G.n_a = 1; G.a_map[0] = static_cast<int16_t>(get_map(lo(sc.act), sc.act, par)); G.a_map[1] = -1; G.n_ops = 1;
+              G.ops[0] = OP(0, C / 8, 0, ii.fold ? C : 0);
+            } else if (ii.fold && kind == 2) {     // folded skip: xh * dW_res -> dy (column 0)
+              G.n_a = 1; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par)); G.a_map[1] = -1; G.n_ops = 1;
               G.ops[0] = OP(0, C / 8, 0, 0);
+            } else if (ii.fold) {   // xh * [..2C rows..] -> (ylo, y0) or (y1, ylo), picked per 3-tap block;  dx' * Wh -> dy
+              G.n_a = 2; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par));
+              G.a_map[1] = static_cast<int16_t>(get_map(dx(sc.act), sc.act, par)); G.n_ops = 2;
+              G.ops[0] = OP(0, 2 * C / 8, 0, 2 * C);
+              G.ops[1] = OP(1, C / 8, C, 0);
             } else {              // xh * [..3C rows..] -> (dy, ylo, y0) or (y1, dy, ylo);  dx * Wh -> dy
               G.n_a = 2; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par));
               G.a_map[1] = static_cast<int16_t>(get_map(dx(sc.act), sc.act, par)); G.n_ops = 2;
@@ -759,7 +899,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           G.tap_rows = static_cast<int16_t>(ii.pair ? ii.nrs / 2 : ii.nrs);
           G.pitch = static_cast<int8_t>(ntaps == 9 ? 10 : 8);
           G.tps = static_cast<int8_t>((k16 && ntaps >= 3) ? 3 : 1);
-          if (!k16 && kind == 1 && lo3) {                              // three lo taps per weight stage
+          if (!k16 && kind >= 1 && lo3) {                              // three lo taps per weight stage
             if (ntaps == 9) G.tps = 3;
             G.tap_rows = static_cast<int16_t>(s.cout / 2);
           }
@@ -767,7 +907,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           cur_kind = k16 ? 0 : kind;
           cur_kd = (ii.acc3 && !k16 && kd > 0) ? kd : 0;
           cur_skip = p.type == T_SKIP1 ? (k16 ? 1 : 2) : 0;
-          G.lo_stage = (cur_kind == 1) ? 1 : 0;
+          G.lo_stage = (cur_kind >= 1) ? 1 : 0;
           fill_ops(G, kind, sc, par, kd);
           if (G.a_map[0] < 0 || (G.n_a == 2 && G.a_map[1] < 0)) bad = true;
           push(G);
@@ -819,6 +959,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
             G.chain = 1; G.phase0 = static_cast<int8_t>(blk & 1);
             blk += (G.ntaps + 2) / 3;
           }
+          mains.insert(mains.end(), g_dwres.begin(), g_dwres.end());   // FOLD: residual skip tangent, accumulates into dy only
           g_main[0] = mains;
           Lc.n_chains = 1 + blk;
         }
@@ -848,6 +989,11 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
       Lc.cout = s.cout; Lc.vel = vel ? 1 : 0; Lc.act = 1;
       Lc.acc3 = ii.acc3 ? 1 : 0;
       Lc.bias = ctx->d_bias + s.bias_off;
+      {
+        const float* fold = ctx->d_fold + (static_cast<size_t>(wb) * nl + li) * 256;
+        Lc.beta = (vel && s.beta_layer >= 0) ? fold : nullptr;
+        Lc.anext = (vel && s.anext_layer >= 0) ? fold + 128 : nullptr;
+      }
       if (!ii.fin) {
         Lc.out_h_ptr = hi(s.out_act);
         Lc.out_l_ptr = split ? lo(s.out_act) : nullptr;
@@ -939,6 +1085,7 @@ cudaError_t launch_conv(int device, int inst, const ConvLaunch* dl, const GroupT
     case I_EARLY_256_512_1: return launch_pair<384, 512, 1, 1>(device, dl, gt, fa, grid, st);
     case I_F192_2: return launch_pair<256, 256, 2, 2>(device, dl, gt, fa, grid, st);
     case I_CHAIN_2: return launch_pair<256, 256, 2, 3>(device, dl, gt, fa, grid, st);
+    case I_FOLD_2: return launch_pair<192, 256, 2, 4>(device, dl, gt, fa, grid, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -1133,6 +1280,8 @@ int nbe_create(nbe_ctx** out, int device) {
   if (const char* e = getenv("NBE_LOBOX")) ctx->lo_box = atoi(e) != 0;
   if (const char* e = getenv("NBE_F192")) ctx->f192 = atoi(e) != 0;
   if (const char* e = getenv("NBE_CHAIN")) ctx->chain = atoi(e) != 0;
+  if (const char* e = getenv("NBE_FOLD")) ctx->fold = atoi(e) != 0;
+  if (const char* e = getenv("NBE_FOLD_AMAX")) ctx->fold_amax = static_cast<float>(atof(e));
   if (const char* e = getenv("NBE_WWIN")) ctx->w_window = atoi(e) != 0;
   if (const char* e = getenv("NBE_TRACE")) ctx->trace = atoi(e) != 0;
   if (const char* e = getenv("NBE_WIDE16")) ctx->wide16 = atoi(e) != 0;
@@ -1150,7 +1299,8 @@ void nbe_destroy(nbe_ctx* ctx) {
   DevGuard dev_guard_(ctx->device);
   cudaDeviceSynchronize();
   for (auto* p : ctx->plans) { if (p->dev_launches) cudaFree(p->dev_launches); delete p; }
-  for (auto& l : ctx->layers) { cudaFree(l.W); cudaFree(l.dW); cudaFree(l.SW); cudaFree(l.sb); }
+  for (auto& l : ctx->layers) { cudaFree(l.W); cudaFree(l.dW); cudaFree(l.SW); cudaFree(l.sb); cudaFree(l.pre_a); cudaFree(l.pre_beta); }
+  cudaFree(ctx->d_fold);
   cudaFree(ctx->d_metas); cudaFree(ctx->d_bias); cudaFree(ctx->d_packed); cudaFree(ctx->d_w32); cudaFree(ctx->d_dw32);
   cudaFree(ctx->d_s0); cudaFree(ctx->d_s1); cudaFree(ctx->arena); cudaFree(ctx->d_ident); cudaFree(ctx->d_box);
   cudaFree(ctx->d_disp); cudaFree(ctx->d_velo); cudaFree(ctx->d_idx);
@@ -1169,6 +1319,7 @@ int nbe_set_precision(nbe_ctx* ctx, int precision) {
   ENTER_DEVICE(ctx);
   if (precision == ctx->precision) return NBE_OK;
   ctx->precision = precision;
+  ctx->fold_active = fold_static_ok(ctx);
   if (ctx->have_params) { CK(cudaDeviceSynchronize()); return build_static(ctx); }
   return NBE_OK;
 }
@@ -1179,7 +1330,7 @@ int nbe_set_params(nbe_ctx* ctx, const nbe_layer_params* layers, int n_layers, i
   ENTER_DEVICE(ctx);
   CK(cudaDeviceSynchronize());
   if (n_layers != 33) return fail(ctx, NBE_ERR_ARG, "expected 33 conv layers, got %d", n_layers);
-  for (auto& l : ctx->layers) { cudaFree(l.W); cudaFree(l.dW); cudaFree(l.SW); cudaFree(l.sb); }
+  for (auto& l : ctx->layers) { cudaFree(l.W); cudaFree(l.dW); cudaFree(l.SW); cudaFree(l.sb); cudaFree(l.pre_a); cudaFree(l.pre_beta); }
   ctx->layers.clear(); ctx->lidx.clear();
   ctx->premod = premodulated != 0; ctx->vel = compute_vel != 0; ctx->eps = eps; ctx->have_params = false;
   for (int i = 0; i < n_layers; ++i) {
@@ -1197,11 +1348,21 @@ int nbe_set_params(nbe_ctx* ctx, const nbe_layer_params* layers, int n_layers, i
     if (!ctx->premod) {
       CK(cudaMalloc(&L.SW, p.cin * 2 * 4)); CK(cudaMemcpy(L.SW, p.style_weight, p.cin * 2 * 4, cudaMemcpyHostToDevice));
       CK(cudaMalloc(&L.sb, p.cin * 4)); CK(cudaMemcpy(L.sb, p.style_bias, p.cin * 4, cudaMemcpyHostToDevice));
+      L.hSW.assign(p.style_weight, p.style_weight + 2 * p.cin);
+      L.hsb.assign(p.style_bias, p.style_bias + p.cin);
+    } else if (ctx->vel && p.dweight && fold_candidate(L)) {
+      std::vector<float> a, beta;
+      factor_premod(L, p.weight, p.dweight, ctx->fold_amax, a, beta);
+      if (L.pre_ok) {
+        CK(cudaMalloc(&L.pre_a, a.size() * 4)); CK(cudaMemcpy(L.pre_a, a.data(), a.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&L.pre_beta, beta.size() * 4)); CK(cudaMemcpy(L.pre_beta, beta.data(), beta.size() * 4, cudaMemcpyHostToDevice));
+      }
     }
     L.bias.assign(p.bias, p.bias + p.cout);
     ctx->lidx[L.block + "/" + L.layer] = static_cast<int>(ctx->layers.size());
     ctx->layers.push_back(L);
   }
+  ctx->fold_active = fold_static_ok(ctx);
   int rc = build_static(ctx);
   if (rc) return rc;
   ctx->have_params = true;
@@ -1215,10 +1376,29 @@ int nbe_modulate(nbe_ctx* ctx, const float* Om, const float* Dz, int batch, void
   if (!ctx->premod && !Om) return fail(ctx, NBE_ERR_ARG, "Om required for style models");
   ENTER_DEVICE(ctx);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // style vector in fp32 as in the reference (style_nbody_emulator_vel_core.py:126-128)
+  std::vector<float> s0(batch), s1(batch);
+  for (int b = 0; b < batch; ++b) {
+    s0[b] = Om ? (Om[b] - 0.3f) * 5.0f : 0.f;
+    s1[b] = Dz[b] - 1.0f;
+  }
+  {
+    // tangent folding divides by the modulation m_i: a cosmology that drives some m_i towards zero falls back to
+    // the 5-product kernels (different weight layout: rebuild the static description)
+    const bool want = fold_static_ok(ctx) && fold_range_ok(ctx, s0, s1);
+    if (want != ctx->fold_active) {
+      CK(cudaDeviceSynchronize());
+      ctx->fold_active = want;
+      int rcs = build_static(ctx);
+      if (rcs) return rcs;
+    }
+  }
   const size_t need_p = static_cast<size_t>(batch) * ctx->packed_halves * 2;
+  const size_t need_f = static_cast<size_t>(batch) * ctx->sl.size() * 256 * 4;
   const size_t need_w = static_cast<size_t>(batch) * ctx->w32_floats * 4;
-  const bool moved = ctx->packed_cap < need_p;
+  const bool moved = ctx->packed_cap < need_p || ctx->fold_cap < need_f;
   int rc;
+  if ((rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_fold), &ctx->fold_cap, need_f))) return rc;
   if ((rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_packed), &ctx->packed_cap, need_p))) return rc;
   if ((rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_w32), &ctx->w32_cap, need_w))) return rc;
   if (ctx->vel) { if ((rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_dw32), &ctx->dw32_cap, need_w))) return rc; }
@@ -1232,12 +1412,7 @@ int nbe_modulate(nbe_ctx* ctx, const float* Om, const float* Dz, int batch, void
     for (auto* p : ctx->plans) { if (p->dev_launches) cudaFree(p->dev_launches); delete p; }
     ctx->plans.clear();
   }
-  // style vector in fp32 as in the reference (style_nbody_emulator_vel_core.py:126-128)
-  std::vector<float> s0(batch), s1(batch);
-  for (int b = 0; b < batch; ++b) {
-    s0[b] = Om ? (Om[b] - 0.3f) * 5.0f : 0.f;
-    s1[b] = Dz[b] - 1.0f;
-  }
+  CK(cudaMemsetAsync(ctx->d_fold, 0, need_f, st));
   CK(cudaMemcpyAsync(ctx->d_s0, s0.data(), batch * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->d_s1, s1.data(), batch * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(ctx->d_packed, 0, need_p, st));
@@ -1255,6 +1430,21 @@ int nbe_modulate(nbe_ctx* ctx, const float* Om, const float* Dz, int batch, void
       M.cout = ly.cout; M.cin = ly.cin; M.k3 = ly.k * ly.k * ly.k;
       M.first = (ly.block == "conv_l00" && (ly.layer == "conv_0" || ly.layer == "skip")) ? 1 : 0;
       M.premod = ctx->premod ? 1 : 0; M.vel = ctx->vel ? 1 : 0;
+      M.fold_SW = nullptr; M.fold_sb = nullptr; M.fold_a = nullptr; M.beta_out = nullptr; M.a_out = nullptr;
+      M.pre_a = ly.pre_a; M.pre_beta = ly.pre_beta;
+      M.beta_layer = p.beta_layer;
+      M.fold_stride = static_cast<int>(ctx->sl.size()) * 256;
+      if (p.fold_layer >= 0) {
+        const Layer& fl = ctx->layers[p.fold_layer];
+        if (ctx->premod) M.fold_a = fl.pre_a; else { M.fold_SW = fl.SW; M.fold_sb = fl.sb; }
+      }
+      const size_t li = static_cast<size_t>(&s - ctx->sl.data());
+      if (s.beta_layer == p.layer) {
+        M.beta_out = ctx->d_fold + li * 256;
+        // its a is the anext of the launch(es) producing the tensor it reads
+        for (size_t lj = 0; lj < ctx->sl.size(); ++lj)
+          if (ctx->sl[lj].anext_layer == p.layer) M.a_out = ctx->d_fold + lj * 256 + 128;
+      }
     }
   if (!ctx->d_metas) CK(cudaMalloc(&ctx->d_metas, hm.size() * sizeof(LayerMeta)));
   CK(cudaMemcpyAsync(ctx->d_metas, hm.data(), hm.size() * sizeof(LayerMeta), cudaMemcpyHostToDevice, st));
@@ -1823,5 +2013,27 @@ long long nbe_debug_read_act(nbe_ctx* ctx, int act, int which, void* host, size_
   if (cudaMemcpy(host, ctx->arena + off, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return NBE_ERR_CUDA;
   return static_cast<long long>(bytes);
 }
+
+
+// Debug: the fold vector a that the producer of activation `act` added to its stored tangent (dx' = dx + a (.) x);
+// zeros when the tensor has none.  Returns the channel count or <0.
+int nbe_debug_act_fold(nbe_ctx* ctx, int act, int sample, float* a_host, int cap) {
+  if (!ctx || !a_host || act < 0 || act >= A_OUT || ctx->plans.empty()) return NBE_ERR_ARG;
+  DevGuard dev_guard_(ctx->device);
+  cudaDeviceSynchronize();
+  const int c = act_channels(act);
+  if (cap < c) return NBE_ERR_ARG;
+  for (int i = 0; i < c; ++i) a_host[i] = 0.f;
+  if (sample < 0 || sample >= ctx->mod_batch) return NBE_ERR_ARG;
+  for (size_t li = 0; li < ctx->sl.size(); ++li)
+    if (ctx->sl[li].out_act == act && ctx->sl[li].anext_layer >= 0 && ctx->vel) {
+      const float* src = ctx->d_fold + (static_cast<size_t>(sample) * ctx->sl.size() + li) * 256 + 128;
+      if (cudaMemcpy(a_host, src, c * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return NBE_ERR_CUDA;
+    }
+  return c;
+}
+
+// 1 when the velocity launches run with the folded tangent (FOLD instances), else 0
+int nbe_fold_active(nbe_ctx* ctx) { return (ctx && ctx->fold_active) ? 1 : 0; }
 
 }  // extern "C"

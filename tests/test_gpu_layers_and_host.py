@@ -52,6 +52,7 @@ def test_every_stored_activation_matches_the_oracle():
         rd, rv = net.forward(P, x, Om, Dz, vf)
     eng = Engine.get()
     worst = {}
+    folded = 0
     for aid, name in enumerate(ACTS):
         rx, rdx = net.cap[name]
         rx = rx[0].permute(1, 2, 3, 0).numpy()
@@ -62,10 +63,15 @@ def test_every_stored_activation_matches_the_oracle():
             continue
         assert hi.shape == rx.shape, (name, hi.shape, rx.shape)
         ex = rel_l2(hi + _read_act(eng, aid, 1), rx)
-        edx = rel_l2(_read_act(eng, aid, 2), rdx[0].permute(1, 2, 3, 0).numpy())
+        # tangent folding: a tensor read by a FOLD launch stores dx' = dx + a (.) x (a of that launch's 3^3 conv)
+        a = np.zeros(rx.shape[-1], dtype=np.float32)
+        assert eng.lib.nbe_debug_act_fold(eng.h, aid, 0, a.ctypes.data_as(C.POINTER(C.c_float)), a.size) == a.size
+        folded += bool(a.any())
+        edx = rel_l2(_read_act(eng, aid, 2), rdx[0].permute(1, 2, 3, 0).numpy() + a * rx)
         worst[name] = (ex, edx)
         assert ex < 1e-5 and edx < 2e-3, (name, ex, edx)
     assert len(worst) == 23
+    assert folded == (13 if eng.lib.nbe_fold_active(eng.h) else 0)
     assert rel_l2(d, rd.numpy()) < 1e-5 and rel_l2(v, rv.numpy()) < 1e-3
 
 
