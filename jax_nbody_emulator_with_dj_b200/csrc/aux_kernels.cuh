@@ -72,7 +72,8 @@ struct LayerMeta {
   const float* pre_a;       // premodulated weights: this layer's own a (cin) / beta (cout) from the host factorisation
   const float* pre_beta;
   float* beta_out;          // main conv of a FOLD launch: beta goes here ([sample][fold_stride])
-  float* a_out;             // ... and a here (the anext of the launch producing its source tensor)
+  float* a_out[2];          // ... and a[a_out_off + j], j < a_out_n, here (the anext of the launch producing a source tensor)
+  int a_out_off[2], a_out_n[2], n_a_out;
   int fold_stride;          // floats between samples in beta_out / a_out
 };
 
@@ -144,10 +145,13 @@ modulate_kernel(const LayerMeta* __restrict__ metas, int n_layers, const float* 
     }
   }
   if (M.vel && M.beta_out != nullptr && threadIdx.x == 0) M.beta_out[static_cast<long long>(b) * M.fold_stride + o] = beta_own;
-  if (M.vel && M.a_out != nullptr && o == 0)
-    for (int i = threadIdx.x; i < M.cin; i += blockDim.x)
-      M.a_out[static_cast<long long>(b) * M.fold_stride + i] =
-          M.premod ? M.pre_a[i] : M.SW[2 * i + 1] / (s0 * M.SW[2 * i] + s1 * M.SW[2 * i + 1] + M.sb[i]);
+  if (M.vel && o == 0)
+    for (int t = 0; t < M.n_a_out; ++t)
+      for (int j = threadIdx.x; j < M.a_out_n[t]; j += blockDim.x) {
+        const int i = j + M.a_out_off[t];
+        M.a_out[t][static_cast<long long>(b) * M.fold_stride + j] =
+            M.premod ? M.pre_a[i] : M.SW[2 * i + 1] / (s0 * M.SW[2 * i] + s1 * M.SW[2 * i + 1] + M.sb[i]);
+      }
   const float inv_Dz = 1.f / (s1 + 1.f);
   const long long sample_off = static_cast<long long>(b) * M.dst_sample_stride;
   const int rowlen = M.kc16 ? 16 : 64;

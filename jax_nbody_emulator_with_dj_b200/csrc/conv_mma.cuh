@@ -79,6 +79,8 @@ struct alignas(128) ConvLaunch {
                             // lo_taps == 3: a 3-D map {64, rows, tiles} whose box carries three consecutive taps
   int32_t lo_rows;          // rows per CTA of a lo stage (0: lo stages use bmap64)
   int32_t lo_taps;          // taps per lo-stage box: 1 or 3
+  int32_t main_rows;        // rows per CTA of a main 64-channel stage (0: the whole stage); the folded 128-output
+                            // instance stages 64 Wh rows per tap and 128 rows [Wl | Wh] per lo tap
   int32_t n_chains;         // EARLY == 3: accumulation chains per item (1 lo chain + the 3-tap blocks of the main groups)
   int32_t n_par;            // 1, or 8 for the x2 up-sampling conv (one parity per item)
   int32_t par_brow_step;    // B rows between parities
@@ -377,6 +379,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
       uint32_t s = 0, ph = 0;
       const int par_brow_step = L->par_brow_step;
       const int lo_rows = L->lo_rows, lo_taps = L->lo_taps;
+      const uint32_t main_rows = L->main_rows > 0 ? static_cast<uint32_t>(L->main_rows) : static_cast<uint32_t>(Cfg::kBRows);
       for (long long it0 = item_first; it0 < n_items; it0 += gridDim.x) {
         int par, w0, h0, d0;
         decode(it0, par, w0, h0, d0);
@@ -384,7 +387,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
           const GroupDesc& G = gt.g[g];
           const bool lo_box = G.lo_stage != 0 && lo_rows > 0;
           const CUtensorMap* bm = G.kc16 ? &L->bmap16 : (lo_box ? &L->bmap64_lo : &L->bmap64);
-          const uint32_t bytes = lo_box ? static_cast<uint32_t>(lo_rows) * 128u : Cfg::kBRows * (G.kc16 ? 32u : 128u);
+          const uint32_t bytes = lo_box ? static_cast<uint32_t>(lo_rows) * 128u : (G.kc16 ? Cfg::kBRows * 32u : main_rows * 128u);
           const int row0 = G.brow0 + par * par_brow_step + (PAIR ? static_cast<int>(rank) * Cfg::kBRows : 0);
           const int tps = G.tps;
           for (int j = 0; j < G.ntaps; j += tps) {
@@ -750,7 +753,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
                 float y1v = s1 * kInvWeightScale + bias_s[c + j + 1];
                 float d0v = __uint_as_float(dy[j]) * kInvWeightScale;
                 float d1v = __uint_as_float(dy[j + 1]) * kInvWeightScale;
-                if constexpr (kFold) {      // + beta_o * (x * W)_o: the demodulation part of x * dW
+                if constexpr (kFold || EARLY == 1) {      // + beta_o * (x * W)_o: the demodulation part of x * dW (beta_s is zero unless folded)
                   d0v = fmaf(beta_s[c + j], s0 * kInvWeightScale, d0v);
                   d1v = fmaf(beta_s[c + j + 1], s1 * kInvWeightScale, d1v);
                 }

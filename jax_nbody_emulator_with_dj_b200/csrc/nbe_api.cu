@@ -31,7 +31,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 enum ConvType { T_CONV3 = 0, T_SKIP1 = 1, T_DOWN = 2, T_UP = 3 };
-enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_PAIR_256_512_1, I_PAIR_128_128_2, I_PAIR_256_256_1, I_PAIR_128_256_1, I_EARLY_128_256_2, I_EARLY_256_512_1, I_F192_2, I_CHAIN_2, I_FOLD_2, I_COUNT };
+enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_PAIR_256_512_1, I_PAIR_128_128_2, I_PAIR_256_256_1, I_PAIR_128_256_1, I_EARLY_128_256_2, I_EARLY_256_512_1, I_F192_2, I_CHAIN_2, I_FOLD_2, I_FOLD128_1, I_COUNT };
 struct InstInfo { int nrs, dc, tm; bool fin; bool pair = false; bool acc3 = false; bool early = false; bool f192 = false; bool chain = false; bool fold = false; };
 const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32, 16, 2, true},
                                  {128, 64, 2, false},  {64, 64, 2, false},   {256, 128, 1, false},
@@ -48,7 +48,10 @@ const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32
                                  // F192 + accumulation chains (EARLY == 3): the two primal accumulators alternate every 3 taps
                                  {256, 256, 2, false, true, true, true, true, true},
                                  // FOLD (EARLY == 4): chains + folded tangent, N = 128 main product, 2 x 96 weight rows per stage
-                                 {192, 256, 2, false, true, true, true, true, true, true}};
+                                 {192, 256, 2, false, true, true, true, true, true, true},
+                                 // folded tangent for the 128-output early-drain instance: 2 x 128 rows per stage
+                                 // (main taps use the first 64: Wh halves; lo taps [Wl | Wh] halves)
+                                 {256, 512, 1, false, true, true, true, false, false, true}};
 
 // activation tensors of the net
 enum ActId {
@@ -60,6 +63,7 @@ struct Src { int act; int crop; int c0; bool kc16; };
 struct ConvPart {
   int layer; int type; int off; std::vector<Src> src; int tile_base64 = 0, tile_base16 = 0;
   int fold_layer = -1;      // layer whose fold vector a is already in the stored tangent of this part's source tensor
+  int fold_off = 0;         // ... input channel i of this part carries a[i + fold_off]
   int beta_layer = -1;      // layer whose beta the owning launch's epilogue applies (-1: none, or this part itself)
 };
 struct StaticLaunch {
@@ -76,6 +80,7 @@ struct StaticLaunch {
   // tangent folding (conv_mma.cuh, ConvLaunch::beta / anext)
   int beta_layer = -1;      // FOLD instance: layer whose beta the epilogue applies (the launch's 3^3 conv)
   int anext_layer = -1;     // layer whose fold vector a the epilogue adds to the stored tangent (fold consumer of out_act)
+  int anext_off = 0;        // ... output channel j gets a[j + anext_off]
 };
 
 struct ActBuf { int c = 0, d = 0, h = 0, w = 0; size_t off_hi = 0, off_lo = 0, off_dx = 0; };
@@ -135,6 +140,7 @@ struct nbe_ctx {
   bool chain = true;        // ... with accumulation chains of 3 taps (NBE_CHAIN=0: one chain per kd-plane)
   bool fold = true;         // ... and the folded tangent (4 instead of 5 products; NBE_FOLD=0 disables)
   bool fold_active = false; // what build_static used: fold && every fold vector in range (checked per modulation)
+  bool fold128 = true;      // ... also in the 128-output launches (NBE_FOLD128=0)
   float fold_amax = 64.f;   // |a_i| above this (a modulation m_i close to zero) switches folding off (NBE_FOLD_AMAX)
   float* d_fold = nullptr; size_t fold_cap = 0;      // [sample][launch][beta 128 | anext 128] floats
   int band_h = 2;           // tile rows per h-band of the item order (NBE_BAND; 0: whole planes)
@@ -232,7 +238,7 @@ int find_layer(nbe_ctx* ctx, const char* block, const char* layer) {
 // ----------------------------------------------------------------------------------------
 // tangent folding: which layers can be the 3^3 conv of a FOLD launch, and whether their fold vectors are usable
 // ----------------------------------------------------------------------------------------
-bool fold_candidate(const Layer& l) { return l.k == 3 && l.cout == 64 && l.cin >= 64; }
+bool fold_candidate(const Layer& l) { return l.k == 3 && l.cout >= 64 && l.cin >= 64; }
 
 // Premodulated weights arrive as (W, dW) without the style parameters.  The reference's modulation gives
 // dW[o,i,t] = W[o,i,t] * (a_i + beta_o) (style_layers_vel.py:86-93): recover a and beta from the per-(o,i) ratio
@@ -359,7 +365,8 @@ int build_static(nbe_ctx* ctx) {
         s.inst = ctx->dbuf ? I_PAIR_128_256_1
                  : (ctx->f192 ? (ctx->chain ? (ctx->fold_active ? I_FOLD_2 : I_CHAIN_2) : I_F192_2)
                               : (ctx->early ? I_EARLY_128_256_2 : I_PAIR_128_256_2));
-      else if (s.inst == I_256_512_1) s.inst = ctx->early ? I_EARLY_256_512_1 : I_PAIR_256_512_1;
+      else if (s.inst == I_256_512_1)
+        s.inst = ctx->early ? ((ctx->fold_active && ctx->fold128) ? I_FOLD128_1 : I_EARLY_256_512_1) : I_PAIR_256_512_1;
       else if (s.inst == I_128_128_2) s.inst = I_PAIR_128_128_2;
       else if (s.inst == I_256_256_1) s.inst = I_PAIR_256_256_1;
     }
@@ -368,26 +375,36 @@ int build_static(nbe_ctx* ctx) {
   // launch producing such a tensor adds a (.) y to the tangent it stores, every other reader subtracts it again
   // in its tangent weights (modulate_kernel)
   {
-    std::vector<int> act_fold(A_COUNT, -1);
+    // channel j of tensor X carries a[j + act_off[X]] of layer act_fold[X] (K-chunk q of that layer reads the 64
+    // channels of its q-th source from c0 on)
+    std::vector<int> act_fold(A_COUNT, -1), act_off(A_COUNT, 0);
     for (auto& s : ctx->sl) {
       if (!kInst[s.inst].fold) continue;
       for (auto& p : s.parts)
         if (p.type == T_CONV3) {
           s.beta_layer = p.layer;
-          for (auto& sc : p.src) {
-            if (act_fold[sc.act] >= 0 && act_fold[sc.act] != p.layer)
+          for (size_t q = 0; q < p.src.size(); ++q) {
+            const Src& sc = p.src[q];
+            const int off = 64 * static_cast<int>(q) - sc.c0;
+            if (act_fold[sc.act] >= 0 && (act_fold[sc.act] != p.layer || act_off[sc.act] != off))
               return fail(ctx, NBE_ERR_STATE, "launch %s: source tensor already has a fold consumer", s.name.c_str());
-            act_fold[sc.act] = p.layer;
+            act_fold[sc.act] = p.layer; act_off[sc.act] = off;
           }
         }
     }
     for (auto& s : ctx->sl) {
-      s.anext_layer = (vel && s.out_act >= 0 && s.out_act < A_COUNT) ? act_fold[s.out_act] : -1;
+      const bool has = vel && s.out_act >= 0 && s.out_act < A_COUNT;
+      s.anext_layer = has ? act_fold[s.out_act] : -1;
+      s.anext_off = has ? act_off[s.out_act] : 0;
       for (auto& p : s.parts) {
+        // this part's input channel i is channel i - 64 q + c0 of its q-th source
         p.fold_layer = act_fold[p.src[0].act];
-        for (auto& sc : p.src)
-          if (act_fold[sc.act] != p.fold_layer)
+        p.fold_off = p.src[0].c0 + act_off[p.src[0].act];
+        for (size_t q = 0; q < p.src.size(); ++q) {
+          const Src& sc = p.src[q];
+          if (act_fold[sc.act] != p.fold_layer || (p.fold_layer >= 0 && sc.c0 - 64 * static_cast<int>(q) + act_off[sc.act] != p.fold_off))
             return fail(ctx, NBE_ERR_STATE, "launch %s: sources with different fold vectors", s.name.c_str());
+        }
         p.beta_layer = (s.beta_layer >= 0 && s.beta_layer != p.layer) ? s.beta_layer : -1;
       }
     }
@@ -460,6 +477,11 @@ int build_static(nbe_ctx* ctx) {
       } else if (ii.fold && k16) {   // 16-channel folded skip of a FOLD launch: N = 2C rows [dW | Wh..] -> (dy, y1)
         prule(EMIT_DW, 0, 0, 0, C, 0, 0);
         prule(EMIT_WH, 0, 0, 1, C, 0, 0); prule(EMIT_WH, 0, 0, 1, C, 0, 3); prule(EMIT_WL, 0, 0, 1, C, 0, 6);
+      } else if (ii.fold && ii.tm == 1) {
+        // 128-output folded instance: main taps stage this CTA's half of Wh (xh * Wh -> y_kd, dx' * Wh -> dy share the
+        // rows), lo taps [Wl half | Wh half] (xh * Wl + xl * Wh -> y0)
+        prule(EMIT_WH, 0, 0, 0, C / 2, 0);
+        prule(EMIT_WL, 1, 0, 0, C / 2, 0);      prule(EMIT_WH, 1, 0, 0, C / 2, C / 2);
       } else if (ii.fold) {
         // per-CTA stage (1.5C rows): rows [0, C) = this CTA's half of the N = 2C operand ([Wl | Wh] -> (ylo, y0) for
         // blocks of phase 0, [Wh | Wl] -> (y1, ylo) for phase 1), rows [C, 1.5C) = its half of Wh for dx' * Wh.
@@ -721,7 +743,9 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
         return n_amap++;
       };
       const int box_rows = ii.pair ? ii.nrs / 2 : ii.nrs;
-      if ((rc = make_b_map(ctx, &Lc.bmap64, packed + s.b64_off, 64, static_cast<long long>(s.n_tiles64) * ii.nrs, box_rows)) ||
+      const bool fold128 = ii.fold && ii.tm == 1;
+      Lc.main_rows = fold128 ? s.cout / 2 : 0;
+      if ((rc = make_b_map(ctx, &Lc.bmap64, packed + s.b64_off, 64, static_cast<long long>(s.n_tiles64) * ii.nrs, fold128 ? s.cout / 2 : box_rows)) ||
           (rc = make_b_map16(ctx, &Lc.bmap16, packed + s.b16_off, s.n_tiles16, ii.nrs, box_rows))) { delete P; return rc; }
       // pair acc3 layout: a lo stage [Wl half | Wh half] fills only the first `cout` of the 1.5 x cout rows
       // each CTA owns per stage; loading just those saves a sixth of the weight traffic
@@ -807,7 +831,11 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
               G.ops[1] = OP(1, C / 8, C / 2, 0);
             } else {
               G.n_a = 2; G.a_map[1] = static_cast<int16_t>(get_map(dx(sc.act), sc.act, par));
-              if (acc3 && kd == 1) {
+              if (ii.fold) {            // xh * Wh -> y_kd (columns 0 / 2C / 3C);  dx' * Wh -> dy (same weight rows)
+                G.n_ops = 2;
+                G.ops[0] = OP(0, C / 8, 0, kd <= 0 ? 0 : (kd == 1 ? 2 * C : 3 * C));
+                G.ops[1] = OP(1, C / 8, 0, C);
+              } else if (acc3 && kd == 1) {
                 G.n_ops = 2;
                 G.ops[0] = OP(0, 2 * C / 8, 0, C);
                 G.ops[1] = OP(1, C / 8, C, C);
@@ -990,7 +1018,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
       Lc.acc3 = ii.acc3 ? 1 : 0;
       Lc.bias = ctx->d_bias + s.bias_off;
       {
-        const float* fold = ctx->d_fold + (static_cast<size_t>(wb) * nl + li) * 256;
+        const float* fold = ctx->d_fold + (static_cast<size_t>(wb) * nl + li) * 256;   // anext is stored with its offset applied
         Lc.beta = (vel && s.beta_layer >= 0) ? fold : nullptr;
         Lc.anext = (vel && s.anext_layer >= 0) ? fold + 128 : nullptr;
       }
@@ -1086,6 +1114,7 @@ cudaError_t launch_conv(int device, int inst, const ConvLaunch* dl, const GroupT
     case I_F192_2: return launch_pair<256, 256, 2, 2>(device, dl, gt, fa, grid, st);
     case I_CHAIN_2: return launch_pair<256, 256, 2, 3>(device, dl, gt, fa, grid, st);
     case I_FOLD_2: return launch_pair<192, 256, 2, 4>(device, dl, gt, fa, grid, st);
+    case I_FOLD128_1: return launch_pair<256, 512, 1, 1>(device, dl, gt, fa, grid, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -1281,6 +1310,7 @@ int nbe_create(nbe_ctx** out, int device) {
   if (const char* e = getenv("NBE_F192")) ctx->f192 = atoi(e) != 0;
   if (const char* e = getenv("NBE_CHAIN")) ctx->chain = atoi(e) != 0;
   if (const char* e = getenv("NBE_FOLD")) ctx->fold = atoi(e) != 0;
+  if (const char* e = getenv("NBE_FOLD128")) ctx->fold128 = atoi(e) != 0;
   if (const char* e = getenv("NBE_FOLD_AMAX")) ctx->fold_amax = static_cast<float>(atof(e));
   if (const char* e = getenv("NBE_WWIN")) ctx->w_window = atoi(e) != 0;
   if (const char* e = getenv("NBE_TRACE")) ctx->trace = atoi(e) != 0;
@@ -1430,20 +1460,27 @@ int nbe_modulate(nbe_ctx* ctx, const float* Om, const float* Dz, int batch, void
       M.cout = ly.cout; M.cin = ly.cin; M.k3 = ly.k * ly.k * ly.k;
       M.first = (ly.block == "conv_l00" && (ly.layer == "conv_0" || ly.layer == "skip")) ? 1 : 0;
       M.premod = ctx->premod ? 1 : 0; M.vel = ctx->vel ? 1 : 0;
-      M.fold_SW = nullptr; M.fold_sb = nullptr; M.fold_a = nullptr; M.beta_out = nullptr; M.a_out = nullptr;
+      M.fold_SW = nullptr; M.fold_sb = nullptr; M.fold_a = nullptr; M.beta_out = nullptr;
       M.pre_a = ly.pre_a; M.pre_beta = ly.pre_beta;
       M.beta_layer = p.beta_layer;
       M.fold_stride = static_cast<int>(ctx->sl.size()) * 256;
+      M.n_a_out = 0;
       if (p.fold_layer >= 0) {
         const Layer& fl = ctx->layers[p.fold_layer];
-        if (ctx->premod) M.fold_a = fl.pre_a; else { M.fold_SW = fl.SW; M.fold_sb = fl.sb; }
+        if (ctx->premod) M.fold_a = fl.pre_a + p.fold_off;
+        else { M.fold_SW = fl.SW + 2 * p.fold_off; M.fold_sb = fl.sb + p.fold_off; }
       }
       const size_t li = static_cast<size_t>(&s - ctx->sl.data());
       if (s.beta_layer == p.layer) {
         M.beta_out = ctx->d_fold + li * 256;
-        // its a is the anext of the launch(es) producing the tensor it reads
+        // its a is the anext of the launch(es) producing the tensor(s) it reads
         for (size_t lj = 0; lj < ctx->sl.size(); ++lj)
-          if (ctx->sl[lj].anext_layer == p.layer) M.a_out = ctx->d_fold + lj * 256 + 128;
+          if (ctx->sl[lj].anext_layer == p.layer && M.n_a_out < 2) {
+            M.a_out[M.n_a_out] = ctx->d_fold + lj * 256 + 128;
+            M.a_out_off[M.n_a_out] = ctx->sl[lj].anext_off;
+            M.a_out_n[M.n_a_out] = act_channels(ctx->sl[lj].out_act);
+            ++M.n_a_out;
+          }
       }
     }
   if (!ctx->d_metas) CK(cudaMalloc(&ctx->d_metas, hm.size() * sizeof(LayerMeta)));
