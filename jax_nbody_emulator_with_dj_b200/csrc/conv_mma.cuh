@@ -178,6 +178,12 @@ struct ConvCfg {
 #endif
 constexpr bool kBaseOffsetMode = NBE_BASE_OFFSET != 0;
 
+// 1: 9-tap 64-channel groups are issued one kw-block (three taps) per elected section; 0: tap by tap
+#ifndef NBE_BLOCK_ISSUE
+#define NBE_BLOCK_ISSUE 1
+#endif
+constexpr bool kBlockIssue = NBE_BLOCK_ISSUE != 0 && !kBaseOffsetMode;
+
 // EARLY (only with the per-kd accumulator layout [y0 | dy | y1 | y2], one TMEM stage): fine-grained
 // accumulator hand-over.  The issuers order an item as  lo products (-> y0) | kd 0 (+ folded skip)
 // -> (y0, dy) | kd 1 -> (dy, y1) | kd 2 -> (y2, dy)  and commit y0_full / y1_full as soon as the
@@ -350,6 +356,8 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
   if (warp == 0) {
     // ------------------------------------------------ A producer (activation blocks)
     if (lane == 0) {
+      for (int g = 0; g < n_groups; ++g)
+        for (int q = 0; q < gt.g[g].n_a; ++q) tensormap_acquire(&L->amap[gt.g[g].a_map[q]]);
       uint32_t s = 0, ph = 0;
       for (long long it0 = item_first; it0 < n_items; it0 += gridDim.x) {
         const long long item = it0 + rank;
@@ -376,6 +384,9 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
   } else if (warp == 1) {
     // ------------------------------------------------ B producer (weight tiles)
     if (lane == 0) {
+      tensormap_acquire(&L->bmap64);
+      tensormap_acquire(&L->bmap16);
+      tensormap_acquire(&L->bmap64_lo);
       uint32_t s = 0, ph = 0;
       const int par_brow_step = L->par_brow_step;
       const int lo_rows = L->lo_rows, lo_taps = L->lo_taps;
@@ -520,6 +531,83 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
             }
             __syncwarp();
             if (++sb == Cfg::kNB) { sb = 0; pb ^= 1; }
+          }
+        } else if (!k16 && ntaps == 9 && kBlockIssue && !FINAL) {
+          // 64-channel rows, 9 taps (kw-major): one elected section per kw-block of three kh taps.  The per-tap
+          // round trip of the generic loop below (wait, elect, reconverge, ring arithmetic: ~400 cycles of dependent
+          // uniform instructions) is as long as the 8 MMAs it brackets take on the tensor pipe once the folded
+          // tangent has removed a fifth of them: the issuers, not the pipe, set the pace.  Here the elected lane waits
+          // for each tap's weight stage itself and hands the stages back one by one, so the ring behaves as before.
+          // Same MMAs into every accumulator in the same order: bit-identical.
+          const uint64_t a_hi64 = static_cast<uint64_t>(desc_hi) << 32;
+          const uint64_t b_hi64 = static_cast<uint64_t>(bdesc_hi) << 32;
+          for (int jb = 0; jb < 3; ++jb) {
+            uint32_t chain_p = 0u, d_sel = op_d[0];
+            bool chain_end = false;
+            if constexpr (kChain) {
+              if (G.chain != 0) {
+                chain_p = (static_cast<uint32_t>(G.phase0) + static_cast<uint32_t>(jb)) & 1u;
+                mbar_wait(chain_p ? y1_empty : y0_empty, ((pe >> chain_p) & 1u) ^ 1u);
+                pe ^= (1u << chain_p);
+                tc_fence_after();
+                d_sel = chain_p ? (kFold ? static_cast<uint32_t>(DC / 4) : 0u) : op_d[0];
+                chain_end = true;
+              }
+            }
+            if (elect_one()) {
+              uint32_t s = sb, p = pb;
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh) {
+                if (tps == 1 || kh == 0) {
+                  mbar_wait(&b_full[s], p);
+                  tc_fence_after();
+                }
+                const uint32_t b_lo = (((smem_u32(b_smem + s * Cfg::kBStage) & 0x3FFFFu) >> 4) +
+                                       (tps == 3 ? static_cast<uint32_t>(kh) * tap16 : 0u)) | (1u << 16);
+#pragma unroll
+                for (int t = 0; t < TM; ++t) {
+                  if ((kIssuers == 2 && t != my_tile) || dead) continue;
+                  const uint32_t d_tile = tmem_u + (buf * TM + t) * DC;
+                  const uint32_t a_row = (static_cast<uint32_t>(t * 16 + kh)) * sbo16 + static_cast<uint32_t>(jb) * row16;
+                  const uint64_t ad0 = a_hi64 | (op_a[0] + a_row), bd0 = b_hi64 | (b_lo + op_b[0]);
+                  const uint64_t ad1 = a_hi64 | (op_a[1] + a_row), bd1 = b_hi64 | (b_lo + op_b[1]);
+                  const uint64_t ad2 = a_hi64 | (op_a[2] + a_row), bd2 = b_hi64 | (b_lo + op_b[2]);
+                  if (n_ops == 2) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      mma(d_tile + d_sel, ad0 + 2u * k, bd0 + 2u * k, op_i[0], 1u);
+                      mma(d_tile + op_d[1], ad1 + 2u * k, bd1 + 2u * k, op_i[1], 1u);
+                    }
+                  } else if (n_ops == 1) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) mma(d_tile + d_sel, ad0 + 2u * k, bd0 + 2u * k, op_i[0], 1u);
+                  } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      mma(d_tile + d_sel, ad0 + 2u * k, bd0 + 2u * k, op_i[0], 1u);
+                      mma(d_tile + op_d[1], ad1 + 2u * k, bd1 + 2u * k, op_i[1], 1u);
+                      mma(d_tile + op_d[2], ad2 + 2u * k, bd2 + 2u * k, op_i[2], 1u);
+                    }
+                  }
+                }
+                if (tps == 1 || kh == 2) {
+                  commit(&b_empty[s]);
+                  if (++s == Cfg::kNB) { s = 0; p ^= 1u; }
+                }
+              }
+              if constexpr (kChain) {
+                if (chain_end) commit(chain_p ? y1_full : y0_full);
+              }
+            }
+            __syncwarp();
+            {   // advance the ring by the stages consumed (the ring may be shorter than three stages)
+              uint32_t adv = sb + (tps == 3 ? 1u : 3u);
+              if constexpr (Cfg::kNB < 3) {
+                if (adv >= Cfg::kNB) { adv -= Cfg::kNB; pb ^= 1u; }
+              }
+              pb ^= (adv >= Cfg::kNB) ? 1u : 0u;
+              sb = (adv >= Cfg::kNB) ? adv - Cfg::kNB : adv;
+            }
           }
         } else
         for (int j = 0, jt = 0; j < ntaps; ++j) {
