@@ -193,7 +193,7 @@ def roofline_from_profile(prof, peak_key="bf16_tflops_sustained"):
             "kernel_share_of_step": dom[1] / tot_t if tot_t else None,
             "net_achieved": tot_f / (tot_t * 1e-3) / 1e12 if tot_t else None,
             "net_frac": tot_f / (tot_t * 1e-3) / 1e12 / peak if tot_t else None,
-            "note": "algorithmic FLOPs (SURVEY 8d) / mean launch duration; split precision executes 5/3 of them"}
+            "note": "algorithmic FLOPs (SURVEY 8d: primal + two tangent products per layer) / mean launch duration; split precision with the folded tangent (DESIGN 4.2) executes 4/3 of them, 5/3 without"}
 
 
 def config2(args):
@@ -502,6 +502,7 @@ def main():
     launches = eng.launch_count(reset=True)
     prof = eng.get_profile()
     eng.set_profiling(False)
+    fold_on = int(eng.lib.nbe_fold_active(eng.h))
     clk = clocks.stop()
     if dist is not None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -524,7 +525,7 @@ def main():
                 "kernel_share_of_step": dom[1] / tot_t if tot_t else None,
                 "net_achieved": tot_f / (tot_t * 1e-3) / 1e12 if tot_t else None,
                 "net_frac": tot_f / (tot_t * 1e-3) / 1e12 / peak if tot_t else None,
-                "note": "algorithmic FLOPs (SURVEY 8d) / mean launch duration; split precision executes 5/3 of them"}
+                "note": "algorithmic FLOPs (SURVEY 8d: primal + two tangent products per layer) / mean launch duration; split precision with the folded tangent (DESIGN 4.2) executes 4/3 of them, 5/3 without"}
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
@@ -633,6 +634,8 @@ def main():
                        "sharding": f"{world} rank(s), contiguous subbox ranges, no data-path collective",
                        "l2": "inputs larger than L2 (1.6 GB box, >10 GB activations per subbox)",
                        "precision": args.precision,
+                       "tangent": "folded: (dx + a.x)*W + beta.(x*W), 4 tensor-core products per layer" if fold_on
+                                  else "x*dW + dx*W, 5 tensor-core products per layer",
                        "baseline_note": "vs_baseline = value / (512^3 / 44.9 s), the reference README's A100-40GB fp32 figure"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "alt_precision": alt, "halo_amortised": amort,
         }
