@@ -222,8 +222,13 @@ constexpr bool kBlockIssue = NBE_BLOCK_ISSUE != 0 && !kBaseOffsetMode;
 // x * dW_res -> dy is a one-tap group of its own with a short weight stage.
 template <int NRS, int DC, int TM, bool FINAL, bool PAIR = false, int EARLY = 0>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupTable gt,
+conv_mma_kernel(const __grid_constant__ ConvLaunch launch, const __grid_constant__ GroupTable gt,
                 const __grid_constant__ FinalArgs fa) {
+  // The launch record (tensor maps included) is a kernel parameter: TMA reads the maps from the constant bank, which
+  // the driver keeps coherent per launch.  (Maps in global memory written by cudaMemcpy would need a
+  // fence.proxy.tensormap::generic.acquire.sys per map and producer thread -- tried: 25 serial fences cost the short
+  // resampling launches 0.1 ms each.)
+  const ConvLaunch* const L = &launch;
   using Cfg = ConvCfg<NRS, DC, TM, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -356,8 +361,6 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
   if (warp == 0) {
     // ------------------------------------------------ A producer (activation blocks)
     if (lane == 0) {
-      for (int g = 0; g < n_groups; ++g)
-        for (int q = 0; q < gt.g[g].n_a; ++q) tensormap_acquire(&L->amap[gt.g[g].a_map[q]]);
       uint32_t s = 0, ph = 0;
       for (long long it0 = item_first; it0 < n_items; it0 += gridDim.x) {
         const long long item = it0 + rank;
@@ -384,9 +387,6 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
   } else if (warp == 1) {
     // ------------------------------------------------ B producer (weight tiles)
     if (lane == 0) {
-      tensormap_acquire(&L->bmap64);
-      tensormap_acquire(&L->bmap16);
-      tensormap_acquire(&L->bmap64_lo);
       uint32_t s = 0, ph = 0;
       const int par_brow_step = L->par_brow_step;
       const int lo_rows = L->lo_rows, lo_taps = L->lo_taps;
@@ -532,7 +532,7 @@ conv_mma_kernel(const ConvLaunch* __restrict__ L, const __grid_constant__ GroupT
             __syncwarp();
             if (++sb == Cfg::kNB) { sb = 0; pb ^= 1; }
           }
-        } else if (!k16 && ntaps == 9 && kBlockIssue && !FINAL) {
+        } else if (!k16 && ntaps == 9 && kBlockIssue && EARLY != 0) {     // the big 3^3 velocity instances only
           // 64-channel rows, 9 taps (kw-major): one elected section per kw-block of three kh taps.  The per-tap
           // round trip of the generic loop below (wait, elect, reconverge, ring arithmetic: ~400 cycles of dependent
           // uniform instructions) is as long as the 8 MMAs it brackets take on the tensor pipe once the folded

@@ -101,7 +101,6 @@ struct Plan {
   size_t arena_bytes = 0;
   std::vector<HostLaunch> launches;   // [sample][launch] flattened
   int n_launch = 0;
-  ConvLaunch* dev_launches = nullptr;
 };
 
 struct Layer {
@@ -580,7 +579,7 @@ int build_static(nbe_ctx* ctx) {
     CK(cudaMemcpy(ctx->d_bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
   // plans depend on the layout: drop them
-  for (auto* p : ctx->plans) { if (p->dev_launches) cudaFree(p->dev_launches); delete p; }
+  for (auto* p : ctx->plans) { delete p; }
   ctx->plans.clear();
   ctx->mod_batch = 0;
   return NBE_OK;
@@ -706,7 +705,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
     rc = ensure(ctx, reinterpret_cast<void**>(&ctx->arena), &ctx->arena_cap, off);
     if (rc) { delete P; return rc; }
     // the arena moved: every cached plan holds stale pointers
-    for (auto* p : ctx->plans) { if (p->dev_launches) cudaFree(p->dev_launches); delete p; }
+    for (auto* p : ctx->plans) { delete p; }
     ctx->plans.clear();
   }
   uint8_t* arena = ctx->arena;
@@ -1043,14 +1042,6 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
       if (ii.pair) H.grid = 2 * static_cast<int>(std::min<long long>((tiles + 1) / 2, ctx->num_sms / 2));
     }
   }
-  // upload
-  {
-    std::vector<ConvLaunch> tmp(P->launches.size());
-    for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = P->launches[i].L;
-    cudaError_t e = cudaMalloc(&P->dev_launches, tmp.size() * sizeof(ConvLaunch));
-    if (e == cudaSuccess) e = cudaMemcpy(P->dev_launches, tmp.data(), tmp.size() * sizeof(ConvLaunch), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { delete P; return fail(ctx, NBE_ERR_CUDA, "plan upload: %s", cudaGetErrorString(e)); }
-  }
   ctx->plans.push_back(P);
   *out = P;
   return NBE_OK;
@@ -1068,7 +1059,7 @@ cudaError_t opt_in_smem(K kern, int bytes, int device, std::atomic<uint64_t>& do
 }
 
 template <int NRS, int DC, int TM, bool FIN>
-cudaError_t launch_inst(int device, const ConvLaunch* dl, const GroupTable& gt, const FinalArgs& fa, int grid, cudaStream_t st) {
+cudaError_t launch_inst(int device, const ConvLaunch& dl, const GroupTable& gt, const FinalArgs& fa, int grid, cudaStream_t st) {
   using Cfg = ConvCfg<NRS, DC, TM>;
   static std::atomic<uint64_t> done{0};
   auto kern = conv_mma_kernel<NRS, DC, TM, FIN>;
@@ -1079,7 +1070,7 @@ cudaError_t launch_inst(int device, const ConvLaunch* dl, const GroupTable& gt, 
 }
 
 template <int NRS, int DC, int TM, int EARLY = 0>
-cudaError_t launch_pair(int device, const ConvLaunch* dl, const GroupTable& gt, const FinalArgs& fa, int grid, cudaStream_t st) {
+cudaError_t launch_pair(int device, const ConvLaunch& dl, const GroupTable& gt, const FinalArgs& fa, int grid, cudaStream_t st) {
   using Cfg = ConvCfg<NRS, DC, TM, true>;
   static std::atomic<uint64_t> done{0};
   auto kern = conv_mma_kernel<NRS, DC, TM, false, true, EARLY>;
@@ -1094,7 +1085,7 @@ cudaError_t launch_pair(int device, const ConvLaunch* dl, const GroupTable& gt, 
   return cudaLaunchKernelEx(&cfg, kern, dl, gt, fa);
 }
 
-cudaError_t launch_conv(int device, int inst, const ConvLaunch* dl, const GroupTable& gt, const FinalArgs& fa, int grid, cudaStream_t st) {
+cudaError_t launch_conv(int device, int inst, const ConvLaunch& dl, const GroupTable& gt, const FinalArgs& fa, int grid, cudaStream_t st) {
   switch (inst) {
     case I_128_128_2: return launch_inst<128, 128, 2, false>(device, dl, gt, fa, grid, st);
     case I_256_256_1: return launch_inst<256, 256, 1, false>(device, dl, gt, fa, grid, st);
@@ -1149,7 +1140,7 @@ int run_sample(nbe_ctx* ctx, Plan* P, int sample, PackArgs pk, FinalArgs fa, cud
   mark();
   for (int li = 0; li < P->n_launch; ++li) {
     const HostLaunch& H = P->launches[static_cast<size_t>(sample) * P->n_launch + li];
-    CK(launch_conv(ctx->device, H.inst, P->dev_launches + static_cast<size_t>(sample) * P->n_launch + li, H.G, fa, H.grid, st));
+    CK(launch_conv(ctx->device, H.inst, H.L, H.G, fa, H.grid, st));
     ctx->launches++;
     mark();
   }
@@ -1328,7 +1319,7 @@ void nbe_destroy(nbe_ctx* ctx) {
   if (!ctx) return;
   DevGuard dev_guard_(ctx->device);
   cudaDeviceSynchronize();
-  for (auto* p : ctx->plans) { if (p->dev_launches) cudaFree(p->dev_launches); delete p; }
+  for (auto* p : ctx->plans) { delete p; }
   for (auto& l : ctx->layers) { cudaFree(l.W); cudaFree(l.dW); cudaFree(l.SW); cudaFree(l.sb); cudaFree(l.pre_a); cudaFree(l.pre_beta); }
   cudaFree(ctx->d_fold);
   cudaFree(ctx->d_metas); cudaFree(ctx->d_bias); cudaFree(ctx->d_packed); cudaFree(ctx->d_w32); cudaFree(ctx->d_dw32);
@@ -1439,7 +1430,7 @@ int nbe_modulate(nbe_ctx* ctx, const float* Om, const float* Dz, int batch, void
   if (moved || batch != ctx->mod_batch) {
     // packed buffer moved or sample count changed: tensor maps are stale
     CK(cudaDeviceSynchronize());
-    for (auto* p : ctx->plans) { if (p->dev_launches) cudaFree(p->dev_launches); delete p; }
+    for (auto* p : ctx->plans) { delete p; }
     ctx->plans.clear();
   }
   CK(cudaMemsetAsync(ctx->d_fold, 0, need_f, st));
@@ -1993,7 +1984,7 @@ int nbe_release_workspace(nbe_ctx* ctx) {
   if (!ctx) return NBE_ERR_ARG;
   ENTER_DEVICE(ctx);
   CK(cudaDeviceSynchronize());
-  for (auto* p : ctx->plans) { if (p->dev_launches) cudaFree(p->dev_launches); delete p; }
+  for (auto* p : ctx->plans) { delete p; }
   ctx->plans.clear();
   cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_cap = 0;
   cudaFree(ctx->d_box); ctx->d_box = nullptr; ctx->box_cap = 0;

@@ -68,14 +68,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
-// A tensor map that lives in GLOBAL memory (written by the host with cudaMemcpy before the launch) is read through
-// the tensormap proxy, whose descriptor cache is not coherent with those writes: a plan rebuilt at an address the
-// allocator has just recycled could otherwise be served a stale descriptor (old base pointers -> illegal address).
-// The acquire fence makes the 128 bytes at `m` visible to the proxy; one per map and producer thread, before its
-// first use.
-__device__ __forceinline__ void tensormap_acquire(const CUtensorMap* m) {
-  asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
-}
 __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
