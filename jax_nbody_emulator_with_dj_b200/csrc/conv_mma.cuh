@@ -893,10 +893,12 @@ conv_mma_kernel(const __grid_constant__ ConvLaunch launch, const __grid_constant
         const bool valid = item_ok && (w < out_w) && (h < out_h);
         if constexpr (FINAL) {
           if (TM == 1 && eg != 0) continue;
-          uint32_t v[16];
-          tmem_ld16(taddr, v);
+          // DC == 16: columns [net | dnet] (displacement-only: [xh*Wh + xl*Wh | xh*Wl]);
+          // DC == 32 (folded tangent): [net | dnet | xh*Wl | -], dnet = (dx + a x)*Wh (+ the skip's residual x*dW_res)
+          uint32_t v[DC >= 32 ? 32 : 16];
+          if constexpr (DC >= 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
           tmem_ld_wait();
-          tmem_st16_zero(taddr);
+          if constexpr (DC >= 32) tmem_st32_zero(taddr); else tmem_st16_zero(taddr);
           if (valid) {
             const int64_t sidx = static_cast<int64_t>(fa.idx_d[d0]) * fa.src_sd +
                                  static_cast<int64_t>(fa.idx_h[h]) * fa.src_sh + fa.idx_w[w];
@@ -906,7 +908,13 @@ conv_mma_kernel(const __grid_constant__ ConvLaunch launch, const __grid_constant
               const float x0 = scale_in_dtype(load_as_f32(fa.src, sidx + c * fa.src_sc, fa.src_dtype),
                                               fa.in_norm, fa.src_dtype);
               float net = __uint_as_float(v[c]) * kInvWeightScale + bias_s[c];
-              if (fa.vel != nullptr) {
+              if constexpr (DC >= 32) {
+                const float prim = (__uint_as_float(v[c]) + __uint_as_float(v[16 + c])) * kInvWeightScale;
+                net = prim + bias_s[c];
+                const float dnet = fmaf(beta_s[c], prim, __uint_as_float(v[8 + c]) * kInvWeightScale);
+                store_from_f32(fa.vel, oidx + c * fa.o_sc, fa.out_dtype,
+                               round_to_dtype(dnet * fa.dx_norm + x0 * fa.x0_norm, fa.mid_dtype));
+              } else if (fa.vel != nullptr) {
                 const float dnet = __uint_as_float(v[8 + c]) * kInvWeightScale;
                 store_from_f32(fa.vel, oidx + c * fa.o_sc, fa.out_dtype,
                                round_to_dtype(dnet * fa.dx_norm + x0 * fa.x0_norm, fa.mid_dtype));

@@ -31,7 +31,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 enum ConvType { T_CONV3 = 0, T_SKIP1 = 1, T_DOWN = 2, T_UP = 3 };
-enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_PAIR_256_512_1, I_PAIR_128_128_2, I_PAIR_256_256_1, I_PAIR_128_256_1, I_EARLY_128_256_2, I_EARLY_256_512_1, I_F192_2, I_CHAIN_2, I_FOLD_2, I_FOLD128_1, I_COUNT };
+enum Inst { I_128_128_2 = 0, I_256_256_1, I_FINAL, I_128_64_2, I_64_64_2, I_256_128_2, I_128_256_2, I_256_512_1, I_PAIR_128_256_2, I_PAIR_256_512_1, I_PAIR_128_128_2, I_PAIR_256_256_1, I_PAIR_128_256_1, I_EARLY_128_256_2, I_EARLY_256_512_1, I_F192_2, I_CHAIN_2, I_FOLD_2, I_FOLD128_1, I_FINAL_FOLD, I_COUNT };
 struct InstInfo { int nrs, dc, tm; bool fin; bool pair = false; bool acc3 = false; bool early = false; bool f192 = false; bool chain = false; bool fold = false; };
 const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32, 16, 2, true},
                                  {128, 64, 2, false},  {64, 64, 2, false},   {256, 128, 1, false},
@@ -51,7 +51,10 @@ const InstInfo kInst[I_COUNT] = {{128, 128, 2, false}, {256, 256, 1, false}, {32
                                  {192, 256, 2, false, true, true, true, true, true, true},
                                  // folded tangent for the 128-output early-drain instance: 2 x 128 rows per stage
                                  // (main taps use the first 64: Wh halves; lo taps [Wl | Wh] halves)
-                                 {256, 512, 1, false, true, true, true, false, false, true}};
+                                 {256, 512, 1, false, true, true, true, false, false, true},
+                                 // last layer with the folded tangent: columns [net | dnet | xh*Wl | -], 48 weight rows per stage
+                                 // ([Wh | dW_res (skip only) | Wl | - ] for xh, [- | Wh] for dx'), three activation reads per tap
+                                 {48, 32, 2, true, false, false, false, false, false, true}};
 
 // activation tensors of the net
 enum ActId {
@@ -139,6 +142,7 @@ struct nbe_ctx {
   bool chain = true;        // ... with accumulation chains of 3 taps (NBE_CHAIN=0: one chain per kd-plane)
   bool fold = true;         // ... and the folded tangent (4 instead of 5 products; NBE_FOLD=0 disables)
   bool fold_active = false; // what build_static used: fold && every fold vector in range (checked per modulation)
+  bool fold_final = true;   // ... and in the last layer (NBE_FOLD_FINAL=0)
   bool fold128 = true;      // ... also in the 128-output launches (NBE_FOLD128=0)
   float fold_amax = 64.f;   // |a_i| above this (a modulation m_i close to zero) switches folding off (NBE_FOLD_AMAX)
   float* d_fold = nullptr; size_t fold_cap = 0;      // [sample][launch][beta 128 | anext 128] floats
@@ -237,7 +241,7 @@ int find_layer(nbe_ctx* ctx, const char* block, const char* layer) {
 // ----------------------------------------------------------------------------------------
 // tangent folding: which layers can be the 3^3 conv of a FOLD launch, and whether their fold vectors are usable
 // ----------------------------------------------------------------------------------------
-bool fold_candidate(const Layer& l) { return l.k == 3 && l.cout >= 64 && l.cin >= 64; }
+bool fold_candidate(const Layer& l) { return l.k == 3 && l.cin >= 64; }
 
 // Premodulated weights arrive as (W, dW) without the style parameters.  The reference's modulation gives
 // dW[o,i,t] = W[o,i,t] * (a_i + beta_o) (style_layers_vel.py:86-93): recover a and beta from the per-(o,i) ratio
@@ -370,6 +374,10 @@ int build_static(nbe_ctx* ctx) {
       else if (s.inst == I_256_256_1) s.inst = I_PAIR_256_256_1;
     }
 
+  if (ctx->fold_active && ctx->fold_final)
+    for (auto& s : ctx->sl)
+      if (s.inst == I_FINAL) s.inst = I_FINAL_FOLD;
+
   // ---- tangent folding: the 3^3 conv of a FOLD launch defines the fold vector of the tensor(s) it reads; the
   // launch producing such a tensor adds a (.) y to the tangent it stores, every other reader subtracts it again
   // in its tangent weights (modulate_kernel)
@@ -426,7 +434,7 @@ int build_static(nbe_ctx* ctx) {
       const bool k16 = p.src[0].kc16;
       const int nkc = static_cast<int>(p.src.size());
       // FOLD: the folded 1^3 skip has a third tile kind, its residual tangent rows (x * dW_res -> dy)
-      const int nk = k16 ? 1 : ((ii.fold && p.type == T_SKIP1) ? 3 : nkind);
+      const int nk = k16 ? 1 : ((ii.fold && !ii.fin && p.type == T_SKIP1) ? 3 : nkind);
       LayerMeta& M = ctx->metas[p.layer];
       int& tb = k16 ? t16 : t64;
       (k16 ? p.tile_base16 : p.tile_base64) = tb;
@@ -465,7 +473,13 @@ int build_static(nbe_ctx* ctx) {
         R.cta_base = static_cast<int8_t>(cta_base); R.kd_mask = static_cast<int8_t>(kdmask);
       };
       const int C = ly.cout;
-      if (ii.fin) {
+      if (ii.fin && ii.fold) {
+        // xh * rows [0, 32) = [Wh | dW_res | Wl | -] -> (net, dnet, ylo, -);  dx' * rows [32, 48) = [- | Wh] -> dnet;
+        // lo tile: xl * rows [0, 16) = [Wh | -] -> net.  dW_res is zero for the 3^3 conv itself (not emitted).
+        rule(EMIT_WH, 0, 0, 0); rule(EMIT_WL, 0, 16, 0); rule(EMIT_WH, 0, 40, 0);
+        if (p.type == T_SKIP1) rule(EMIT_DW, 0, 8, 0);
+        rule(EMIT_WH, 1, 0, 0);
+      } else if (ii.fin) {
         if (vel) {
           rule(EMIT_WH, 0, 0, 0); rule(EMIT_DW, 0, 8, 0); rule(EMIT_WH, 0, 24, 0);
           if (split) { rule(EMIT_WL, 1, 0, 0); rule(EMIT_WH, 1, 16, 0); }
@@ -783,7 +797,7 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
         const Layer& ly = ctx->layers[p.layer];
         const int nkc = static_cast<int>(p.src.size());
         const bool k16 = p.src[0].kc16;
-        const int nk = k16 ? 1 : ((ii.fold && p.type == T_SKIP1) ? 3 : nkind);
+        const int nk = k16 ? 1 : ((ii.fold && !ii.fin && p.type == T_SKIP1) ? 3 : nkind);
         const int C = ly.cout;
         const int tb = k16 ? p.tile_base16 : p.tile_base64;
         // OP(a, n8, b_row, d_col) -> device layout with byte offsets >> 4 precomputed
@@ -859,6 +873,20 @@ int build_plan(nbe_ctx* ctx, const int32_t dims[3], int batch, Plan** out) {
           }
           const __half* pl = split ? lo(sc.act) : nullptr;
           const __half* pd = vel ? dx(sc.act) : nullptr;
+          if (ii.fin && ii.fold) {
+            if (kind == 0) {
+              G.n_a = 2; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par));
+              G.a_map[1] = static_cast<int16_t>(get_map(pd, sc.act, par));
+              G.n_ops = 2;
+              G.ops[0] = OP(0, 4, 0, 0);
+              G.ops[1] = OP(1, 2, 32, 0);
+            } else {
+              G.n_a = 1; G.a_map[0] = static_cast<int16_t>(get_map(pl, sc.act, par)); G.a_map[1] = -1;
+              G.n_ops = 1;
+              G.ops[0] = OP(0, 2, 0, 0);
+            }
+            return;
+          }
           if (ii.fin) {
             if (vel) {
               G.n_a = 2; G.a_map[0] = static_cast<int16_t>(get_map(ph, sc.act, par));
@@ -1106,6 +1134,7 @@ cudaError_t launch_conv(int device, int inst, const ConvLaunch& dl, const GroupT
     case I_CHAIN_2: return launch_pair<256, 256, 2, 3>(device, dl, gt, fa, grid, st);
     case I_FOLD_2: return launch_pair<192, 256, 2, 4>(device, dl, gt, fa, grid, st);
     case I_FOLD128_1: return launch_pair<256, 512, 1, 1>(device, dl, gt, fa, grid, st);
+    case I_FINAL_FOLD: return launch_inst<48, 32, 2, true>(device, dl, gt, fa, grid, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -1302,6 +1331,7 @@ int nbe_create(nbe_ctx** out, int device) {
   if (const char* e = getenv("NBE_CHAIN")) ctx->chain = atoi(e) != 0;
   if (const char* e = getenv("NBE_FOLD")) ctx->fold = atoi(e) != 0;
   if (const char* e = getenv("NBE_FOLD128")) ctx->fold128 = atoi(e) != 0;
+  if (const char* e = getenv("NBE_FOLD_FINAL")) ctx->fold_final = atoi(e) != 0;
   if (const char* e = getenv("NBE_FOLD_AMAX")) ctx->fold_amax = static_cast<float>(atof(e));
   if (const char* e = getenv("NBE_WWIN")) ctx->w_window = atoi(e) != 0;
   if (const char* e = getenv("NBE_TRACE")) ctx->trace = atoi(e) != 0;

@@ -71,7 +71,7 @@ def test_every_stored_activation_matches_the_oracle():
         worst[name] = (ex, edx)
         assert ex < 1e-5 and edx < 2e-3, (name, ex, edx)
     assert len(worst) == 23
-    assert folded == (19 if eng.lib.nbe_fold_active(eng.h) else 0)
+    assert folded == (20 if eng.lib.nbe_fold_active(eng.h) else 0)
     assert rel_l2(d, rd.numpy()) < 1e-5 and rel_l2(v, rv.numpy()) < 1e-3
 
 
