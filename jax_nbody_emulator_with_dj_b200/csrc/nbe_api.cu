@@ -216,7 +216,11 @@ struct DevGuard {
   cudaError_t err;
   explicit DevGuard(int dev) {
     if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    err = (prev == dev) ? cudaSuccess : cudaSetDevice(dev);
+    // always: cudaGetDevice reports device 0 in a thread that has no context bound yet, and the first CUDA call of
+    // such a thread may be a DRIVER call (cuTensorMapEncodeTiled in build_plan, once every buffer is already
+    // allocated) -- CUDA_ERROR_INVALID_CONTEXT on the second box of a two-GPU process_box_multi
+    err = cudaSetDevice(dev);
+    if (prev == dev) prev = -1;
   }
   ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
