@@ -319,16 +319,17 @@ conv_mma_kernel(const __grid_constant__ ConvLaunch launch, const __grid_constant
   // a pair walks the item list two at a time (leader takes the even one); both CTAs of a pair
   // therefore run the same number of iterations
   const long long item_first = PAIR ? static_cast<long long>(blockIdx.x & ~1u) : static_cast<long long>(blockIdx.x);
-  // Item order (slowest to fastest): parity, h-band, d, tile row inside the band, tile column.
+  // Item order (slowest to fastest): h-band, d, tile row inside the band, tile column, parity.
   // The CTAs in flight then cover a narrow band over several d planes, so the three input planes
   // a 3^3 tap window re-reads stay L2-resident between their uses.
   const int band_h = (L->band_h > 0 && L->band_h < tiles_h) ? L->band_h : tiles_h;
-  const long long per_par = 1ll * out_d * tiles_h * tiles_w;
   const long long band_items = 1ll * out_d * band_h * tiles_w;
   const int n_bands = (tiles_h + band_h - 1) / band_h;
   auto decode = [&](long long item, int& par, int& w0, int& h0, int& d0) {
-    par = static_cast<int>(item / per_par);
-    long long r = item - par * per_par;
+    // x2 up-sampling: the 8 output parities of one input tile are CONSECUTIVE items (they run on 8 CTAs at the same
+    // time), so the input tile is read from DRAM once and the interleaved output lines are completed together
+    par = n_par > 1 ? static_cast<int>(item % n_par) : 0;
+    long long r = n_par > 1 ? item / n_par : item;
     int band = static_cast<int>(r / band_items);
     if (band > n_bands - 1) band = n_bands - 1;
     r -= band * band_items;
