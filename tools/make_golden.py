@@ -4,8 +4,9 @@ the fixtures travel to the GPU box, the oracle run does not have to.
     python tools/make_golden.py [name ...]
 
 Inputs are regenerated from seeds inside the tests; only the oracle outputs are stored.
-NOTE: the reference itself (JAX) cannot run in this image, so these are oracle outputs
-("parity unpinned" at network level, see oracle/__init__.py)."""
+NOTE: these are oracle outputs.  tools/make_reference_golden.py produces the same cases with the
+reference's own sources (over oracle/jaxshim) and tests/test_oracle_vs_reference.py checks the
+two sets of files against each other (1e-12)."""
 import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, '.')

@@ -96,7 +96,7 @@ def g_ref_n104():
 def g_ref_batch2():
     """Per-sample cosmologies through the reference's vmap branch (style_layers_vel.py:129-141)."""
     x = field((2, 3, 104, 104, 104), 77)
-    z, Om = np.array([0.0, 2.0], np.float32), np.array([0.1, 0.5], np.float32)
+    z, Om = [0.0, 2.0], [0.1, 0.5]          # python floats, as tools/make_golden.py passes them
     out = dict(seed=77, z=z, Om=Om)
     out["disp"], out["vel"] = run_style_vel(x, z, Om, True)
     out["disp32"], out["vel32"] = run_style_vel(x, z, Om, False)
