@@ -31,8 +31,7 @@ def field(shape, seed):
 
 def load(golden_dir, name):
     p = os.path.join(golden_dir, name + ".npz")
-    if not os.path.exists(p):
-        pytest.skip(f"{name}.npz not generated yet (tools/make_reference_golden.py {name})")
+    assert os.path.exists(p), f"{p} missing: run tools/make_reference_golden.py {name} in the build container"
     return np.load(p)
 
 
