@@ -129,6 +129,16 @@ def test_committed_oracle_fixtures_equal_reference_outputs(golden_dir, ours, the
     assert ed32 < 5e-6 and ev32 < 3e-3, (ed32, ev32)
 
 
+def test_production_geometry_truth_blocks_equal_reference_outputs(golden_dir):
+    """The fp64 truth the 224^3 GPU gate uses (n224_block_225.npz: 32^3 output blocks computed from 128^3 input windows,
+    stored as float32) against the reference run on the same windows."""
+    g, r = load(golden_dir, "n224_block_225"), load(golden_dir, "ref_n224_blocks")
+    assert int(g["seed"]) == int(r["seed"]) == 225 and np.array_equal(g["offsets"], r["offsets"])
+    for b in range(2):
+        assert np.array_equal(g["disp"][b], r["disp"][b].astype(np.float32)) or rel_l2(g["disp"][b], r["disp"][b]) < 1e-7
+        assert rel_l2(g["vel"][b], r["vel"][b]) < 1e-7
+
+
 def test_reference_variants_agree_with_each_other(golden_dir):
     """Style, premodulated+vel and premodulated models of the reference on the n104 input (fp32): the same
     displacement / velocity as StyleNBodyEmulatorVelCore (not tested anywhere in the reference's own suite)."""

@@ -121,6 +121,19 @@ def g_ref_n128():
     return out
 
 
+def g_ref_n224_blocks():
+    """Two 32^3 blocks of the 224^3 -> 128^3 PRODUCTION subbox (seed 225: one corner, one centre) from the reference in
+    fp64 on the 128^3 input windows behind them — the construction of the oracle fixture n224_block_225.npz (VALID
+    convolutions are translation-consistent; a whole 224^3 fp64 run does not fit 62 GB)."""
+    x = field((1, 3, 224, 224, 224), 225)
+    offsets = [(0, 0, 0), (48, 48, 48)]
+    ds, vs = [], []
+    for (a, b, c) in offsets:
+        d, v = run_style_vel(x[:, :, a:a + 128, b:b + 128, c:c + 128], 0.5, 0.3, True)
+        ds.append(d[0]), vs.append(v[0])
+    return dict(disp=np.stack(ds), vel=np.stack(vs), offsets=np.array(offsets, np.int32), seed=225, N=224, z=0.5, Om=0.3)
+
+
 KEEP_FULL = (("conv_l00", "conv_0"), ("conv_l00", "skip"), ("down_l0", "conv_0"), ("up_r2", "conv_0"),
              ("conv_r2", "skip"), ("conv_r01", "conv_1"))
 
@@ -240,7 +253,8 @@ def g_ref_layers():
 
 
 ALL = dict(ref_cosmology=g_ref_cosmology, ref_layers=g_ref_layers, ref_modulation=g_ref_modulation, ref_n104=g_ref_n104,
-           ref_batch2=g_ref_batch2, ref_noncubic=g_ref_noncubic, ref_box=g_ref_box, ref_n128=g_ref_n128, ref_box16=g_ref_box16)
+           ref_batch2=g_ref_batch2, ref_noncubic=g_ref_noncubic, ref_box=g_ref_box, ref_n128=g_ref_n128, ref_box16=g_ref_box16,
+           ref_n224_blocks=g_ref_n224_blocks)
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or ALL):
