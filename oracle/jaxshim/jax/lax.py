@@ -14,9 +14,13 @@ def conv_general_dilated(lhs, rhs, window_strides, padding, lhs_dilation=None, r
     if dimension_numbers is not None:
         assert tuple(dimension_numbers) == ("NCDHW", "OIDHW", "NCDHW"), dimension_numbers
     assert feature_group_count == 1 and batch_group_count == 1
-    x = torch.from_numpy(_np.ascontiguousarray(_np.asarray(lhs)))
-    w = torch.from_numpy(_np.ascontiguousarray(_np.asarray(rhs)))
-    assert x.dtype == w.dtype, (x.dtype, w.dtype)          # jax.lax requires equal operand dtypes
+    lhs, rhs = _np.asarray(lhs), _np.asarray(rhs)
+    assert lhs.dtype == rhs.dtype, (lhs.dtype, rhs.dtype)  # jax.lax requires equal operand dtypes
+    narrow = lhs.dtype if lhs.dtype.name in ("float16", "bfloat16") else None
+    if narrow is not None:                                  # torch-CPU has no 16-bit conv3d: fp32 math, rounded result
+        lhs, rhs = lhs.astype(_np.float32), rhs.astype(_np.float32)
+    x = torch.from_numpy(_np.ascontiguousarray(lhs))
+    w = torch.from_numpy(_np.ascontiguousarray(rhs))
     nd = x.dim() - 2
     assert nd == 3
     if lhs_dilation is not None and tuple(lhs_dilation) != (1,) * nd:
@@ -34,13 +38,8 @@ def conv_general_dilated(lhs, rhs, window_strides, padding, lhs_dilation=None, r
             flat += [lo, hi]
         x = F.pad(x, flat)
     rd = tuple(rhs_dilation) if rhs_dilation is not None else 1
-    half = x.dtype == torch.float16
-    if half:                                                # torch-CPU has no fp16 conv3d
-        x, w = x.float(), w.float()
-    y = F.conv3d(x, w, None, stride=tuple(window_strides), dilation=rd)
-    if half:
-        y = y.half()
-    return _canon(y.numpy())
+    y = F.conv3d(x, w, None, stride=tuple(window_strides), dilation=rd).numpy()
+    return _canon(y.astype(narrow) if narrow is not None else y)
 
 
 def rsqrt(x):

@@ -8,6 +8,11 @@ float16, float32, float64 = _np.float16, _np.float32, _np.float64
 int8, int16, int32, int64 = _np.int8, _np.int16, _np.int32, _np.int64
 uint8, uint32 = _np.uint8, _np.uint32
 bool_ = _np.bool_
+try:                                    # numpy has no bf16 of its own; ml_dtypes provides the scalar type
+    import ml_dtypes as _ml
+    bfloat16 = _ml.bfloat16
+except ImportError:                     # pragma: no cover
+    pass
 complex64 = _np.complex64
 pi, inf, nan, newaxis, e = _np.pi, _np.inf, _np.nan, None, _np.e
 dtype = _np.dtype
