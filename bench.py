@@ -556,8 +556,8 @@ def main():
     # supplementary: halo-amortising tiling (bit-identical output, fewer halo FLOPs), SURVEY 8(f1)
     amort = None
     if (S, nd) == (512, 4) and not args.no_alt:
-        try:
-            mcfg, (mc, ma, mp) = proc.merged_config((2, 2, 1))
+        def timed_merge(merge):
+            mcfg, (mc, ma, mp) = proc.merged_config(merge)
             mlo, mhi = shard_range(int(mcfg.n_subboxes), rank, world)
             def step_m():
                 eng.process_box_dev(box_dev, mcfg.size, mcfg.crop_size, mp, mc, ma, mlo, mhi - mlo, Dz, vf, disp_dev, vel_dev)
@@ -567,8 +567,18 @@ def main():
             t_m = torch.tensor([m0.elapsed_time(m1)], device="cuda")
             if dist is not None:
                 dist.all_reduce(t_m, op=dist.ReduceOp.MAX)
-            amort = {"merge": [2, 2, 1], "subboxes": int(mcfg.n_subboxes), "value": particles_total / (float(t_m.item()) * 1e-3),
-                     "unit": "particles/s", "note": "same box and output bits; 16 tiles 352x352x224 -> 256x256x128 instead of 64 x 224^3 -> 128^3"}
+            return int(mcfg.n_subboxes), particles_total / (float(t_m.item()) * 1e-3)
+        try:
+            n221, v221 = timed_merge((2, 2, 1))
+            amort = {"merge": [2, 2, 1], "subboxes": n221, "value": v221, "unit": "particles/s",
+                     "note": "same box and output bits; 16 tiles 352x352x224 -> 256x256x128 instead of 64 x 224^3 -> 128^3"}
+            try:                        # 8 tiles 352^3 -> 256^3 (about 120 GB of HBM with the other arenas of this run)
+                n222, v222 = timed_merge((2, 2, 2))
+                amort = {"merge": [2, 2, 2], "subboxes": n222, "value": v222, "unit": "particles/s",
+                         "note": "same box and output bits; 8 tiles 352^3 -> 256^3 instead of 64 x 224^3 -> 128^3",
+                         "merge_221": {"subboxes": n221, "value": v221}}
+            except Exception as e:
+                amort["merge_222_error"] = str(e)[:200]
         except Exception as e:          # e.g. not enough HBM for the larger arena
             amort = {"error": str(e)[:200]}
 
