@@ -179,14 +179,17 @@ def ref_pkg():
     saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("jax", "flax", "jax_nbody_emulator")}
     for k in saved:
         del sys.modules[k]
-    sys.path[:0] = [os.path.join(ROOT, "oracle", "jaxshim"), REF_SRC]
+    added = [os.path.join(ROOT, "oracle", "jaxshim"), REF_SRC]
+    sys.path[:0] = added
     try:
         import jax
         assert jax.__version__.endswith("shim")
         import jax_nbody_emulator as ref
         yield ref
     finally:
-        del sys.path[:2]
+        for a in added:
+            if a in sys.path:
+                sys.path.remove(a)
         for k in [k for k in sys.modules if k.split(".")[0] in ("jax", "flax", "jax_nbody_emulator")]:
             del sys.modules[k]
         sys.modules.update(saved)
