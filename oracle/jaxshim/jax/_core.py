@@ -76,6 +76,12 @@ class Array(np.ndarray):
         res = getattr(ufunc, method)(*ins, **kwargs)
         if out is not None:
             return out[0] if len(out) == 1 else out
+        # JAX's weak typing: bf16 array (op) python scalar stays bf16.  numpy does this itself for its own float16
+        # (NEP 50) but promotes ml_dtypes' bfloat16 to float32.
+        arrs = [i for i in ins if isinstance(i, np.ndarray)]
+        if (arrs and all(a.dtype.name == "bfloat16" for a in arrs) and isinstance(res, np.ndarray) and res.dtype == np.float32
+                and all(isinstance(i, (np.ndarray, int, float)) for i in ins)):
+            res = res.astype(arrs[0].dtype)
         return canon(res)
 
     def __setitem__(self, k, v):
